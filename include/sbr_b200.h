@@ -1,0 +1,153 @@
+/*
+ * sbr_b200.h -- C ABI of the B200-native sequence-recommender training engine.
+ *
+ * This is the drop-in boundary for the `fit()` / `predict()` hot path of maciejkula/sbr-rs
+ * (reference @ f01d4a7, citations are into /root/reference/src/).  The reference has no FFI of its own;
+ * every entry point below states the Rust item it replaces, and INTEGRATION.md shows the `extern "C"`
+ * block and the safe wrappers a maintainer of the Rust crate would add to bind it.
+ *
+ * Conventions
+ *  - `usize` ids (lib.rs:77-81 UserId/ItemId/Timestamp) cross the ABI as uint64_t.
+ *  - Every constructor returns an owned opaque handle, released by the matching *_free (Rust Drop).
+ *  - No exceptions / panics cross the ABI: all failures are sbr_status codes; Rust index panics
+ *    (out-of-range ids) surface as SBR_ERR_INVALID_ARGUMENT.  sbr_last_error_string() gives detail.
+ *  - All pointers are HOST pointers unless a name says `_device`.  Parameters and optimizer state live in
+ *    HBM for the lifetime of the model and persist across fit() calls (warm restart, benches/benchmark.rs:40-42).
+ *  - There is NO CPU fallback: every compute entry point returns SBR_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SBR_B200_H
+#define SBR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SBR_OK = 0,
+    SBR_ERR_NO_INTERACTIONS = 1,    /* FittingError::NoInteractions        lib.rs:93-97, sequence_model.rs:86-88 */
+    SBR_ERR_INVALID_PREDICTION = 2, /* PredictionError::InvalidPredictionValue lib.rs:85-89, sequence_model.rs:225-229 */
+    SBR_ERR_INVALID_ARGUMENT = 3,   /* replaces Rust bounds / chunks_mut(0) panics */
+    SBR_ERR_CUDA = 4,
+    SBR_ERR_NCCL = 5,
+    SBR_ERR_UNSUPPORTED = 6
+} sbr_status;
+
+/* models/mod.rs:16-23 */
+typedef enum { SBR_LOSS_BPR = 0, SBR_LOSS_HINGE = 1, SBR_LOSS_WARP = 2 } sbr_loss;
+/* models/mod.rs:27-32 */
+typedef enum { SBR_OPTIMIZER_ADAGRAD = 0, SBR_OPTIMIZER_ADAM = 1 } sbr_optimizer;
+/* models/mod.rs:36-41 */
+typedef enum { SBR_PARALLELISM_ASYNCHRONOUS = 0, SBR_PARALLELISM_SYNCHRONOUS = 1 } sbr_parallelism;
+/* models/lstm.rs:29-35 */
+typedef enum { SBR_LSTM_NORMAL = 0, SBR_LSTM_COUPLED = 1 } sbr_lstm_variant;
+
+typedef struct sbr_compressed sbr_compressed;           /* data.rs:228-234 CompressedInteractions */
+typedef struct sbr_hyperparameters sbr_hyperparameters; /* lstm.rs:39-52 / ewma.rs:45-57 Hyperparameters */
+typedef struct sbr_model sbr_model;                     /* lstm.rs:387-389 ImplicitLSTMModel / ewma.rs:402-404 */
+typedef struct sbr_fit_plan sbr_fit_plan;               /* device-resident schedule of one fit() (no Rust analogue) */
+
+const char* sbr_last_error_string(void);
+/* number of usable sm_100 devices; 0 when none (compute entry points then fail with SBR_ERR_CUDA) */
+int sbr_device_count(void);
+/* one process per GPU: select the device this process (all later handles) uses. Default 0. */
+sbr_status sbr_set_device(int device);
+
+/* ------------------------------------------------------------------ data.rs ------------------------------- */
+/* Interactions::to_compressed (data.rs:180-182, 236-265): stable sort by (user, timestamp), histogram, prefix sum. */
+sbr_status sbr_compressed_from_triplets(const uint64_t* user_ids, const uint64_t* item_ids, const uint64_t* timestamps,
+                                        size_t nnz, size_t num_users, size_t num_items, sbr_compressed** out);
+/* Adopt an existing CSR (the three Vec fields at data.rs:231-233). timestamps may be NULL. Copies. */
+sbr_status sbr_compressed_from_csr(const uint64_t* user_pointers, const uint64_t* item_ids, const uint64_t* timestamps,
+                                   size_t num_users, size_t num_items, sbr_compressed** out);
+size_t sbr_compressed_num_users(const sbr_compressed* c); /* data.rs:293-295 */
+size_t sbr_compressed_num_items(const sbr_compressed* c); /* data.rs:298-300 */
+size_t sbr_compressed_len(const sbr_compressed* c);
+/* borrow the CSR arrays (valid until free): to_interactions (data.rs:308-328) / iter_users (data.rs:269-274) */
+sbr_status sbr_compressed_borrow(const sbr_compressed* c, const uint64_t** user_pointers, const uint64_t** item_ids,
+                                 const uint64_t** timestamps);
+/* CompressedInteractionsUser::chunks (data.rs:363-371, 406-432): first chunk smallest.  Writes up to `cap`
+ * (start, len) pairs relative to the user's slice and the total count to *n. */
+sbr_status sbr_compressed_user_chunks(const sbr_compressed* c, size_t user_id, size_t chunk_size, uint64_t* starts,
+                                      uint64_t* lens, size_t cap, size_t* n);
+/* Pre-stage the item-id stream in HBM (otherwise done lazily by the first fit/mrr call that needs it). */
+sbr_status sbr_compressed_upload(sbr_compressed* c);
+void sbr_compressed_free(sbr_compressed* c);
+
+/* ------------------------------------------------- lstm.rs:54-202 / ewma.rs:59-206 ------------------------ */
+sbr_hyperparameters* sbr_lstm_hyperparameters_new(size_t num_items, size_t max_sequence_length); /* lstm.rs:56-71 */
+sbr_hyperparameters* sbr_ewma_hyperparameters_new(size_t num_items, size_t max_sequence_length); /* ewma.rs:61-76 */
+sbr_status sbr_hyper_learning_rate(sbr_hyperparameters* h, float v);      /* lstm.rs:74-77 */
+sbr_status sbr_hyper_l2_penalty(sbr_hyperparameters* h, float v);         /* lstm.rs:80-83 */
+sbr_status sbr_hyper_embedding_dim(sbr_hyperparameters* h, size_t v);     /* lstm.rs:86-89 */
+sbr_status sbr_hyper_num_epochs(sbr_hyperparameters* h, size_t v);        /* lstm.rs:92-95 */
+sbr_status sbr_hyper_loss(sbr_hyperparameters* h, sbr_loss v);            /* lstm.rs:98-101 */
+sbr_status sbr_hyper_lstm_variant(sbr_hyperparameters* h, sbr_lstm_variant v); /* lstm.rs:104-107 (LSTM only) */
+/* lstm.rs:110-113.  On the GPU `num_threads` is the number of Hogwild partitions (one warp each) that train
+ * concurrently; 0 = auto (fill the device).  1 reproduces the reference's single-thread update order exactly. */
+sbr_status sbr_hyper_num_threads(sbr_hyperparameters* h, size_t v);
+sbr_status sbr_hyper_parallelism(sbr_hyperparameters* h, sbr_parallelism v); /* lstm.rs:116-119 */
+sbr_status sbr_hyper_from_seed(sbr_hyperparameters* h, const uint8_t seed[16]); /* lstm.rs:129-132 */
+sbr_status sbr_hyper_optimizer(sbr_hyperparameters* h, sbr_optimizer v);  /* lstm.rs:135-138 */
+void sbr_hyper_free(sbr_hyperparameters* h);
+/* Hyperparameters::build(self) (lstm.rs:197-201 / ewma.rs:201-205): consumes `h` (also on failure). */
+sbr_status sbr_hyper_build(sbr_hyperparameters* h, sbr_model** out);
+
+/* ---------------------------------------------------------- models ---------------------------------------- */
+/* ImplicitLSTMModel::fit / ImplicitEWMAModel::fit (lstm.rs:395-397, ewma.rs:408-410 -> sequence_model.rs:70-178). */
+sbr_status sbr_model_fit(sbr_model* m, const sbr_compressed* interactions, float* loss_out);
+/* OnlineRankingModel::user_representation (sequence_model.rs:182-211): state after the last
+ * max_sequence_length ids.  out has embedding_dim floats. */
+sbr_status sbr_model_user_representation(const sbr_model* m, const uint64_t* item_ids, size_t n, float* out);
+/* batched variant: users given as CSR slices ptr[u]..ptr[u+1] of item_ids; out is [num_users, embedding_dim] */
+sbr_status sbr_model_user_representations(const sbr_model* m, const uint64_t* ptr, const uint64_t* item_ids,
+                                          size_t num_users, float* out);
+/* OnlineRankingModel::predict (sequence_model.rs:213-232) */
+sbr_status sbr_model_predict(const sbr_model* m, const float* user, const uint64_t* item_ids, size_t k, float* out);
+/* evaluation::mrr_score (evaluation.rs:12-48) */
+sbr_status sbr_model_mrr_score(const sbr_model* m, const sbr_compressed* test, float* out);
+/* ParameterNode::index (lstm.rs:272-283): bit-exact row gather, out is [n, embedding_dim] */
+sbr_status sbr_model_gather_rows(const sbr_model* m, const uint64_t* item_ids, size_t n, float* out);
+
+size_t sbr_model_embedding_dim(const sbr_model* m);
+size_t sbr_model_num_items(const sbr_model* m);
+/* Parameter exchange (the serde surface, lstm.rs:204-210).  Names: "item_embeddings" [N*D], "item_biases" [N],
+ * "lstm_weights" [2D*4*D] (row k of [h,x], gate f/i/g/o, unit d), "lstm_biases" [4*D], "alpha" [D];
+ * optimizer state with suffix ".s1" (Adagrad sum of squares / Adam m) and ".s2" (Adam v). */
+sbr_status sbr_model_parameter_len(const sbr_model* m, const char* name, size_t* len);
+sbr_status sbr_model_get_parameter(const sbr_model* m, const char* name, float* out, size_t len);
+sbr_status sbr_model_set_parameter(sbr_model* m, const char* name, const float* data, size_t len);
+sbr_status sbr_model_get_num_updates(const sbr_model* m, uint64_t* out); /* Adam step counter */
+sbr_status sbr_model_set_num_updates(sbr_model* m, uint64_t v);
+/* Hyperparameters.rng (lstm.rs:49, serialised with the model): xorshift128 state x,y,z,w */
+sbr_status sbr_model_get_rng_state(const sbr_model* m, uint32_t out[4]);
+sbr_status sbr_model_set_rng_state(sbr_model* m, const uint32_t state[4]);
+void sbr_model_free(sbr_model* m);
+
+/* ------------------------------------------- device-resident fit schedule --------------------------------- */
+typedef struct {
+    uint64_t steps;          /* optimizer steps = sub-sequences processed (sequence_model.rs:111) */
+    uint64_t timesteps;      /* the reference's `examples` counter (sequence_model.rs:158) */
+    uint64_t partitions;     /* concurrent Hogwild partitions actually used */
+    uint64_t kernel_launches;
+    uint64_t h2d_bytes, d2h_bytes;
+    double train_kernel_ms;  /* CUDA-event time of the training kernel(s) on the engine's stream */
+    double total_device_ms;  /* CUDA-event time from first H2D to last D2H */
+    double host_prepare_ms;  /* sub-sequence build + shuffle + partitioning on the host */
+} sbr_fit_stats;
+
+/* Split of sbr_model_fit into "stage once" + "run": create does sequence_model.rs:74-98 (sub-sequences, shuffle,
+ * partitions, per-partition rngs) and puts everything in HBM; run does :100-175 for num_epochs epochs. */
+sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* interactions, sbr_fit_plan** out);
+sbr_status sbr_fit_plan_run(sbr_fit_plan* p, float* loss_out);
+sbr_status sbr_fit_plan_stats(const sbr_fit_plan* p, sbr_fit_stats* out);
+void sbr_fit_plan_free(sbr_fit_plan* p);
+/* stats of the most recent sbr_model_fit on this model */
+sbr_status sbr_model_last_fit_stats(const sbr_model* m, sbr_fit_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,777 @@
+// api.cu -- host side of the engine and the C ABI declared in include/sbr_b200.h.
+//
+// Mirrors, in C++ (no Rust toolchain in this image), the reference's host logic for the fit()/predict() path:
+//   data.rs:213-265,406-432      CompressedInteractions (stable sort, CSR, first-chunk-smallest chunker)
+//   sequence_model.rs:70-98      sub-sequence build, master shuffle, partitioning, per-partition rngs
+//   lstm.rs:54-202 / ewma.rs     Hyperparameters builder and defaults
+// and drives the sm_100a kernels.  There is no CPU compute path: without a usable device every compute entry
+// point fails with SBR_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sbr_b200.h"
+#include "engine.h"
+
+using namespace sbr;
+
+namespace {
+
+thread_local std::string g_err;
+int g_device = 0;
+
+sbr_status fail(sbr_status s, const std::string& msg) { g_err = msg; return s; }
+sbr_status cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return SBR_ERR_CUDA;
+}
+#define CU(expr)                                                      \
+    do {                                                              \
+        cudaError_t e__ = (expr);                                     \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #expr);         \
+    } while (0)
+
+struct DeviceInfo { bool ok = false; int sms = 0; std::string why; };
+
+DeviceInfo& device_info() {
+    static DeviceInfo info;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n <= 0) { info.why = "no CUDA device available (this library has no CPU fallback)"; cudaGetLastError(); return; }
+        if (g_device >= n) { info.why = "selected device index out of range"; return; }
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, g_device) != cudaSuccess) { info.why = "cudaGetDeviceProperties failed"; return; }
+        if (p.major != 10) { info.why = "device is not sm_100 (B200): kernels are built for sm_100a only"; return; }
+        info.sms = p.multiProcessorCount;
+        info.ok = true;
+    });
+    return info;
+}
+
+sbr_status require_device() {
+    DeviceInfo& d = device_info();
+    if (!d.ok) return fail(SBR_ERR_CUDA, d.why);
+    CU(cudaSetDevice(g_device));
+    return SBR_OK;
+}
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// pinned double-buffer used to narrow usize ids to u32 on the way to HBM
+struct Staging {
+    static constexpr size_t kElems = 8u << 20;  // 32 MiB per buffer
+    uint32_t* buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    bool ready = false;
+    std::mutex mu;
+    sbr_status init() {
+        if (ready) return SBR_OK;
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaHostAlloc(&buf[i], kElems * sizeof(uint32_t), cudaHostAllocDefault));
+            CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        ready = true;
+        return SBR_OK;
+    }
+};
+Staging g_staging;
+
+// narrow + upload n ids (optionally validating < bound); dst is device memory
+sbr_status upload_ids_u32(const uint64_t* src, size_t n, uint32_t* dst, cudaStream_t st, uint64_t bound, size_t* h2d_bytes) {
+    std::lock_guard<std::mutex> lk(g_staging.mu);
+    sbr_status s = g_staging.init();
+    if (s) return s;
+    size_t done = 0; int b = 0; bool used[2] = {false, false};
+    while (done < n) {
+        const size_t cnt = std::min(Staging::kElems, n - done);
+        if (used[b]) CU(cudaEventSynchronize(g_staging.ev[b]));
+        uint32_t* out = g_staging.buf[b];
+        uint64_t bad = 0;
+        for (size_t i = 0; i < cnt; ++i) { const uint64_t v = src[done + i]; bad |= (uint64_t)(v >= bound); out[i] = (uint32_t)v; }
+        if (bad) return fail(SBR_ERR_INVALID_ARGUMENT, "item id out of range");
+        CU(cudaMemcpyAsync(dst + done, out, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(g_staging.ev[b], st));
+        used[b] = true; b ^= 1; done += cnt;
+    }
+    for (int i = 0; i < 2; ++i) if (used[i]) CU(cudaEventSynchronize(g_staging.ev[i]));
+    if (h2d_bytes) *h2d_bytes += n * sizeof(uint32_t);
+    return SBR_OK;
+}
+
+}  // namespace
+
+// ============================================================================================================
+// handles
+// ============================================================================================================
+struct sbr_compressed {
+    size_t num_users = 0, num_items = 0;
+    std::vector<uint64_t> user_ptr, item_ids, timestamps;
+    // lazily created HBM mirror (immutable data => safe to share between const users)
+    mutable std::mutex mu;
+    mutable uint32_t* d_item_ids = nullptr;
+    mutable uint64_t* d_user_ptr = nullptr;
+    mutable size_t upload_bytes = 0;  // bytes moved by the most recent upload (0 if it was already resident)
+    ~sbr_compressed() {
+        if (d_item_ids) cudaFree(d_item_ids);
+        if (d_user_ptr) cudaFree(d_user_ptr);
+    }
+};
+
+struct sbr_hyperparameters {
+    int model = MODEL_LSTM;
+    size_t num_items = 0, max_sequence_length = 0, embedding_dim = 16;   // lstm.rs:58-60
+    float learning_rate = 0.01f, l2_penalty = 0.0f;                      // lstm.rs:61-62
+    int lstm_variant = SBR_LSTM_COUPLED, loss = SBR_LOSS_BPR;            // lstm.rs:63-64
+    int optimizer = SBR_OPTIMIZER_ADAM, parallelism = SBR_PARALLELISM_SYNCHRONOUS;  // lstm.rs:65-66
+    uint8_t seed[16];
+    size_t num_threads = 0;                                              // lstm.rs:68 (0 = fill the device)
+    size_t num_epochs = 10;                                              // lstm.rs:69
+};
+
+struct sbr_model {
+    sbr_hyperparameters h;
+    ModelDev dev{};
+    XorShift rng{};          // Hyperparameters.rng (lstm.rs:49), advanced by every fit (sequence_model.rs:84,97)
+    uint64_t num_updates = 0;
+    cudaStream_t stream = nullptr;
+    mutable std::mutex mu;
+    sbr_fit_stats last{};
+    ~sbr_model() {
+        if (dev.E) cudaFree(dev.E);
+        if (dev.B) cudaFree(dev.B);
+        if (dev.dense) cudaFree(dev.dense);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+struct sbr_fit_plan {
+    sbr_model* model = nullptr;
+    PlanDev dev{};
+    uint64_t* d_seq_start = nullptr; uint32_t* d_seq_len = nullptr;
+    size_t nsub = 0, P = 0, n = 0;
+    uint64_t steps_per_run = 0, timesteps_per_epoch = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    sbr_fit_stats stats{};
+    ~sbr_fit_plan() {
+        if (d_seq_start) cudaFree(d_seq_start);
+        if (d_seq_len) cudaFree(d_seq_len);
+        if (dev.order) cudaFree(dev.order);
+        if (dev.rng) cudaFree(dev.rng);
+        if (dev.keys) cudaFree(dev.keys);
+        if (dev.step_ctr) cudaFree(dev.step_ctr);
+        if (dev.loss_acc) cudaFree(dev.loss_acc);
+        if (dev.examples) cudaFree(dev.examples);
+        if (dev.scratch) cudaFree(dev.scratch);
+        for (cudaEvent_t e : {ev0, ev1, evk0, evk1}) if (e) cudaEventDestroy(e);
+    }
+};
+
+namespace {
+
+sbr_status ensure_uploaded(const sbr_compressed* c, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->upload_bytes = 0;
+    if (c->d_item_ids || c->item_ids.empty()) return SBR_OK;
+    sbr_status s = require_device();
+    if (s) return s;
+    uint32_t* d = nullptr; uint64_t* dp = nullptr;
+    CU(cudaMalloc(&d, std::max<size_t>(c->item_ids.size(), 1) * sizeof(uint32_t)));
+    size_t bytes = 0;
+    s = upload_ids_u32(c->item_ids.data(), c->item_ids.size(), d, st, c->num_items, &bytes);
+    if (s) { cudaFree(d); return s; }
+    if (cudaMalloc(&dp, c->user_ptr.size() * sizeof(uint64_t)) != cudaSuccess) { cudaFree(d); return cuda_fail(cudaGetLastError(), "cudaMalloc user_ptr"); }
+    cudaError_t e = cudaMemcpyAsync(dp, c->user_ptr.data(), c->user_ptr.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaFree(d); cudaFree(dp); return cuda_fail(e, "upload user_ptr"); }
+    bytes += c->user_ptr.size() * sizeof(uint64_t);
+    c->d_item_ids = d; c->d_user_ptr = dp; c->upload_bytes = bytes;
+    return SBR_OK;
+}
+
+struct ParamRef { int kind; int slot; size_t off, len; };  // kind 0: E rows, 1: bias, 2: dense
+
+sbr_status resolve_param(const sbr_model* m, const char* name, ParamRef* out) {
+    std::string base(name); int slot = 0;
+    if (base.size() > 3 && (base.compare(base.size() - 3, 3, ".s1") == 0 || base.compare(base.size() - 3, 3, ".s2") == 0)) {
+        slot = base[base.size() - 1] - '0'; base.resize(base.size() - 3);
+    }
+    const size_t N = m->dev.N, D = m->dev.D;
+    if (slot >= m->dev.S && !(slot <= 2 && base != "item_embeddings")) return fail(SBR_ERR_INVALID_ARGUMENT, "optimizer state slot not present for this optimizer");
+    if (slot == 2 && m->dev.opt != 1) return fail(SBR_ERR_INVALID_ARGUMENT, "'.s2' exists only for Adam");
+    if (base == "item_embeddings") { *out = {0, slot, 0, N * D}; return SBR_OK; }
+    if (base == "item_biases") { *out = {1, slot, 0, N}; return SBR_OK; }
+    if (m->dev.model == MODEL_LSTM && base == "lstm_weights") { *out = {2, slot, 0, 2 * D * 4 * D}; return SBR_OK; }
+    if (m->dev.model == MODEL_LSTM && base == "lstm_biases") { *out = {2, slot, 2 * D * 4 * D, 4 * D}; return SBR_OK; }
+    if (m->dev.model == MODEL_EWMA && base == "alpha") { *out = {2, slot, 0, D}; return SBR_OK; }
+    return fail(SBR_ERR_INVALID_ARGUMENT, std::string("unknown parameter name: ") + name);
+}
+
+}  // namespace
+
+// ============================================================================================================
+// C ABI
+// ============================================================================================================
+extern "C" {
+
+const char* sbr_last_error_string(void) { return g_err.c_str(); }
+
+int sbr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+sbr_status sbr_set_device(int device) {
+    if (device < 0) return fail(SBR_ERR_INVALID_ARGUMENT, "negative device index");
+    g_device = device;
+    return SBR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ data.rs --
+sbr_status sbr_compressed_from_triplets(const uint64_t* user_ids, const uint64_t* item_ids, const uint64_t* timestamps,
+                                        size_t nnz, size_t num_users, size_t num_items, sbr_compressed** out) {
+    if (!out || (nnz && (!user_ids || !item_ids || !timestamps))) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if (num_items > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "num_items must fit in 32 bits");
+    for (size_t i = 0; i < nnz; ++i) {
+        if (user_ids[i] >= num_users) return fail(SBR_ERR_INVALID_ARGUMENT, "user id >= num_users");
+        if (item_ids[i] >= num_items) return fail(SBR_ERR_INVALID_ARGUMENT, "item id >= num_items");
+    }
+    sbr_compressed* c = new (std::nothrow) sbr_compressed();
+    if (!c) return fail(SBR_ERR_INVALID_ARGUMENT, "out of memory");
+    c->num_users = num_users; c->num_items = num_items;
+    // data.rs:240 `data.sort_by(cmp_timestamp)`: STABLE sort on (user, timestamp); ties keep input order
+    std::vector<uint64_t> idx(nnz);
+    for (size_t i = 0; i < nnz; ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) {
+        if (user_ids[a] != user_ids[b]) return user_ids[a] < user_ids[b];
+        return timestamps[a] < timestamps[b];
+    });
+    c->user_ptr.assign(num_users + 1, 0);
+    c->item_ids.resize(nnz); c->timestamps.resize(nnz);
+    for (size_t i = 0; i < nnz; ++i) {  // data.rs:246-251
+        const uint64_t s = idx[i];
+        c->item_ids[i] = item_ids[s]; c->timestamps[i] = timestamps[s];
+        c->user_ptr[user_ids[s] + 1] += 1;
+    }
+    for (size_t u = 1; u <= num_users; ++u) c->user_ptr[u] += c->user_ptr[u - 1];  // data.rs:253-255
+    *out = c;
+    return SBR_OK;
+}
+
+sbr_status sbr_compressed_from_csr(const uint64_t* user_pointers, const uint64_t* item_ids, const uint64_t* timestamps,
+                                   size_t num_users, size_t num_items, sbr_compressed** out) {
+    if (!out || !user_pointers) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if (num_items > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "num_items must fit in 32 bits");
+    if (user_pointers[0] != 0) return fail(SBR_ERR_INVALID_ARGUMENT, "user_pointers[0] must be 0");
+    for (size_t u = 0; u < num_users; ++u)
+        if (user_pointers[u + 1] < user_pointers[u]) return fail(SBR_ERR_INVALID_ARGUMENT, "user_pointers must be non-decreasing");
+    const size_t nnz = user_pointers[num_users];
+    if (nnz && !item_ids) return fail(SBR_ERR_INVALID_ARGUMENT, "null item_ids");
+    sbr_compressed* c = new (std::nothrow) sbr_compressed();
+    if (!c) return fail(SBR_ERR_INVALID_ARGUMENT, "out of memory");
+    c->num_users = num_users; c->num_items = num_items;
+    c->user_ptr.assign(user_pointers, user_pointers + num_users + 1);
+    c->item_ids.assign(item_ids, item_ids + nnz);   // range-checked when narrowed for upload
+    if (timestamps) c->timestamps.assign(timestamps, timestamps + nnz);
+    else c->timestamps.assign(nnz, 0);
+    *out = c;
+    return SBR_OK;
+}
+
+size_t sbr_compressed_num_users(const sbr_compressed* c) { return c ? c->num_users : 0; }
+size_t sbr_compressed_num_items(const sbr_compressed* c) { return c ? c->num_items : 0; }
+size_t sbr_compressed_len(const sbr_compressed* c) { return c ? c->item_ids.size() : 0; }
+
+sbr_status sbr_compressed_borrow(const sbr_compressed* c, const uint64_t** user_pointers, const uint64_t** item_ids,
+                                 const uint64_t** timestamps) {
+    if (!c) return fail(SBR_ERR_INVALID_ARGUMENT, "null handle");
+    if (user_pointers) *user_pointers = c->user_ptr.data();
+    if (item_ids) *item_ids = c->item_ids.data();
+    if (timestamps) *timestamps = c->timestamps.data();
+    return SBR_OK;
+}
+
+sbr_status sbr_compressed_user_chunks(const sbr_compressed* c, size_t user_id, size_t chunk_size, uint64_t* starts,
+                                      uint64_t* lens, size_t cap, size_t* n) {
+    if (!c || !n) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if (user_id >= c->num_users) return fail(SBR_ERR_INVALID_ARGUMENT, "user id out of range");  // data.rs:278-280
+    if (chunk_size == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "chunk_size must be > 0");
+    const size_t len = c->user_ptr[user_id + 1] - c->user_ptr[user_id];
+    size_t idx = 0, k = 0;
+    while (idx < len) {  // data.rs:406-432
+        const size_t mod = (len - idx) % chunk_size;
+        const size_t cs = mod == 0 ? chunk_size : mod;
+        if (k < cap) { if (starts) starts[k] = idx; if (lens) lens[k] = cs; }
+        idx += cs; ++k;
+    }
+    *n = k;
+    return SBR_OK;
+}
+
+sbr_status sbr_compressed_upload(sbr_compressed* c) {
+    if (!c) return fail(SBR_ERR_INVALID_ARGUMENT, "null handle");
+    sbr_status s = require_device();
+    if (s) return s;
+    return ensure_uploaded(c, nullptr);
+}
+
+void sbr_compressed_free(sbr_compressed* c) { delete c; }
+
+// ----------------------------------------------------------------------------------------- hyperparameters --
+static sbr_hyperparameters* hyper_new(int model, size_t num_items, size_t max_sequence_length) {
+    sbr_hyperparameters* h = new (std::nothrow) sbr_hyperparameters();
+    if (!h) return nullptr;
+    h->model = model; h->num_items = num_items; h->max_sequence_length = max_sequence_length;
+    // lstm.rs:67 seeds from thread_rng(); here: wall clock mixed with the address (call sbr_hyper_from_seed to pin)
+    uint64_t s = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count() ^ (uint64_t)(uintptr_t)h;
+    for (int i = 0; i < 16; ++i) { s = s * 6364136223846793005ULL + 1442695040888963407ULL; h->seed[i] = (uint8_t)(s >> 56); }
+    return h;
+}
+sbr_hyperparameters* sbr_lstm_hyperparameters_new(size_t n, size_t t) { return hyper_new(MODEL_LSTM, n, t); }
+sbr_hyperparameters* sbr_ewma_hyperparameters_new(size_t n, size_t t) { return hyper_new(MODEL_EWMA, n, t); }
+
+#define HYPER_SETTER(name, type, field, check)                                                      \
+    sbr_status name(sbr_hyperparameters* h, type v) {                                               \
+        if (!h) return fail(SBR_ERR_INVALID_ARGUMENT, "null hyperparameters");                      \
+        if (!(check)) return fail(SBR_ERR_INVALID_ARGUMENT, #name ": value out of range");          \
+        h->field = v;                                                                               \
+        return SBR_OK;                                                                              \
+    }
+HYPER_SETTER(sbr_hyper_learning_rate, float, learning_rate, std::isfinite(v))
+HYPER_SETTER(sbr_hyper_l2_penalty, float, l2_penalty, std::isfinite(v))
+HYPER_SETTER(sbr_hyper_embedding_dim, size_t, embedding_dim, v > 0)
+HYPER_SETTER(sbr_hyper_num_epochs, size_t, num_epochs, true)
+HYPER_SETTER(sbr_hyper_loss, sbr_loss, loss, v >= 0 && v <= 2)
+HYPER_SETTER(sbr_hyper_num_threads, size_t, num_threads, true)
+HYPER_SETTER(sbr_hyper_parallelism, sbr_parallelism, parallelism, v >= 0 && v <= 1)
+HYPER_SETTER(sbr_hyper_optimizer, sbr_optimizer, optimizer, v >= 0 && v <= 1)
+
+sbr_status sbr_hyper_lstm_variant(sbr_hyperparameters* h, sbr_lstm_variant v) {
+    if (!h) return fail(SBR_ERR_INVALID_ARGUMENT, "null hyperparameters");
+    if (h->model != MODEL_LSTM) return fail(SBR_ERR_INVALID_ARGUMENT, "lstm_variant applies to LSTM hyperparameters only");
+    if (v < 0 || v > 1) return fail(SBR_ERR_INVALID_ARGUMENT, "bad lstm variant");
+    h->lstm_variant = v;
+    return SBR_OK;
+}
+sbr_status sbr_hyper_from_seed(sbr_hyperparameters* h, const uint8_t seed[16]) {
+    if (!h || !seed) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    std::memcpy(h->seed, seed, 16);
+    return SBR_OK;
+}
+void sbr_hyper_free(sbr_hyperparameters* h) { delete h; }
+
+sbr_status sbr_hyper_build(sbr_hyperparameters* hp, sbr_model** out) {
+    if (!hp || !out) { delete hp; return fail(SBR_ERR_INVALID_ARGUMENT, "null argument"); }
+    sbr_hyperparameters h = *hp;
+    delete hp;  // build(self) consumes
+    if (h.num_items == 0 || h.num_items > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "num_items must be in [1, 2^32)");
+    if (h.max_sequence_length < 1 || h.max_sequence_length > 65535) return fail(SBR_ERR_INVALID_ARGUMENT, "max_sequence_length must be in [1, 65535]");
+    sbr_status s = require_device();
+    if (s) return s;
+    sbr_model* m = new (std::nothrow) sbr_model();
+    if (!m) return fail(SBR_ERR_INVALID_ARGUMENT, "out of memory");
+    m->h = h;
+    ModelDev& d = m->dev;
+    d.model = h.model; d.variant = h.lstm_variant; d.loss = h.loss; d.opt = h.optimizer;
+    d.N = (uint32_t)h.num_items; d.D = (int)h.embedding_dim; d.T = (int)h.max_sequence_length;
+    d.S = h.optimizer == SBR_OPTIMIZER_ADAM ? 3 : 2;
+    d.lr = h.learning_rate; d.l2 = h.l2_penalty;
+    d.ndense = h.model == MODEL_LSTM ? (size_t)2 * d.D * 4 * d.D + 4 * d.D : (size_t)d.D;
+    const char* why = nullptr;
+    if (!train_supported(d, &why)) { delete m; return fail(SBR_ERR_UNSUPPORTED, why); }
+    xs_from_seed(m->rng, h.seed);
+    auto bail = [&](cudaError_t e, const char* what) { sbr_status r = cuda_fail(e, what); delete m; return r; };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaMalloc(&d.E, (size_t)d.N * d.S * d.D * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc item table");
+    if ((e = cudaMalloc(&d.B, (size_t)d.N * sizeof(float4))) != cudaSuccess) return bail(e, "cudaMalloc bias table");
+    if ((e = cudaMalloc(&d.dense, 3 * d.ndense * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc dense parameters");
+    // parameter init (lstm.rs:174-186): embeddings N(0, 1/D) in HBM, biases 0, alpha 0, LSTM U(+-1/sqrt(D)) [wyrm-recalled]
+    const uint64_t seed64 = xs_next_u64(m->rng);
+    if ((e = launch_init_embeddings(d, seed64, m->stream)) != cudaSuccess) return bail(e, "init embeddings");
+    std::vector<float> dense(3 * d.ndense, 0.0f);
+    if (h.model == MODEL_LSTM) {
+        const double a = 1.0 / std::sqrt((double)d.D);
+        for (size_t i = 0; i < d.ndense; ++i) {
+            const double u = ((double)(xs_next_u64(m->rng) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+            dense[i] = (float)((2.0 * u - 1.0) * a);
+        }
+    }
+    if ((e = cudaMemcpyAsync(d.dense, dense.data(), dense.size() * sizeof(float), cudaMemcpyHostToDevice, m->stream)) != cudaSuccess) return bail(e, "upload dense");
+    if ((e = cudaStreamSynchronize(m->stream)) != cudaSuccess) return bail(e, "build sync");
+    *out = m;
+    return SBR_OK;
+}
+
+size_t sbr_model_embedding_dim(const sbr_model* m) { return m ? (size_t)m->dev.D : 0; }
+size_t sbr_model_num_items(const sbr_model* m) { return m ? (size_t)m->dev.N : 0; }
+void sbr_model_free(sbr_model* m) { if (m) { cudaSetDevice(g_device); delete m; } }
+
+sbr_status sbr_model_parameter_len(const sbr_model* m, const char* name, size_t* len) {
+    if (!m || !name || !len) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    ParamRef r; sbr_status s = resolve_param(m, name, &r);
+    if (s) return s;
+    *len = r.len;
+    return SBR_OK;
+}
+
+static sbr_status param_io(sbr_model* m, const char* name, float* host, size_t len, bool set) {
+    if (!m || !name || !host) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    sbr_status s = require_device();
+    if (s) return s;
+    ParamRef r; s = resolve_param(m, name, &r);
+    if (s) return s;
+    if (len != r.len) return fail(SBR_ERR_INVALID_ARGUMENT, "parameter length mismatch");
+    std::lock_guard<std::mutex> lk(m->mu);
+    cudaStream_t st = m->stream;
+    if (r.kind == 2) {
+        float* p = m->dev.dense + (size_t)r.slot * m->dev.ndense + r.off;
+        if (set) CU(cudaMemcpyAsync(p, host, len * sizeof(float), cudaMemcpyHostToDevice, st));
+        else CU(cudaMemcpyAsync(host, p, len * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return SBR_OK;
+    }
+    float* tmp = nullptr;
+    CU(cudaMalloc(&tmp, len * sizeof(float)));
+    cudaError_t e = cudaSuccess;
+    if (set) {
+        e = cudaMemcpyAsync(tmp, host, len * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = r.kind == 0 ? launch_pack_rows(m->dev, r.slot, tmp, st) : launch_pack_bias(m->dev, r.slot, tmp, st);
+    } else {
+        e = r.kind == 0 ? launch_unpack_rows(m->dev, r.slot, tmp, st) : launch_unpack_bias(m->dev, r.slot, tmp, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host, tmp, len * sizeof(float), cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return cuda_fail(e, "parameter transfer");
+    return SBR_OK;
+}
+
+sbr_status sbr_model_get_parameter(const sbr_model* m, const char* name, float* out, size_t len) {
+    return param_io(const_cast<sbr_model*>(m), name, out, len, false);
+}
+sbr_status sbr_model_set_parameter(sbr_model* m, const char* name, const float* data, size_t len) {
+    return param_io(m, name, const_cast<float*>(data), len, true);
+}
+sbr_status sbr_model_get_num_updates(const sbr_model* m, uint64_t* out) {
+    if (!m || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = m->num_updates;
+    return SBR_OK;
+}
+sbr_status sbr_model_set_num_updates(sbr_model* m, uint64_t v) {
+    if (!m) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    m->num_updates = v;
+    return SBR_OK;
+}
+
+sbr_status sbr_model_get_rng_state(const sbr_model* m, uint32_t out[4]) {
+    if (!m || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    out[0] = m->rng.x; out[1] = m->rng.y; out[2] = m->rng.z; out[3] = m->rng.w;
+    return SBR_OK;
+}
+sbr_status sbr_model_set_rng_state(sbr_model* m, const uint32_t state[4]) {
+    if (!m || !state) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if ((state[0] | state[1] | state[2] | state[3]) == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "xorshift state must not be all zero");
+    m->rng.x = state[0]; m->rng.y = state[1]; m->rng.z = state[2]; m->rng.w = state[3];
+    return SBR_OK;
+}
+
+// --------------------------------------------------------------------------------------------------- fit ----
+sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_plan** out) {
+    if (!m || !c || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    sbr_status s = require_device();
+    if (s) return s;
+    if (c->num_items > m->dev.N) return fail(SBR_ERR_INVALID_ARGUMENT, "interactions.num_items exceeds the model's num_items");
+    const double t0 = now_ms();
+    const size_t T = (size_t)m->dev.T;
+    // sequence_model.rs:76-83: chunk every user, keep len > 2
+    std::vector<uint64_t> starts; std::vector<uint32_t> lens;
+    uint64_t timesteps = 0;
+    for (size_t u = 0; u < c->num_users; ++u) {
+        const size_t b = c->user_ptr[u], len = c->user_ptr[u + 1] - b;
+        size_t idx = 0;
+        while (idx < len) {
+            const size_t mod = (len - idx) % T;
+            const size_t cs = mod == 0 ? T : mod;
+            if (cs > 2) { starts.push_back(b + idx); lens.push_back((uint32_t)cs); }
+            idx += cs;
+        }
+    }
+    const size_t nsub = starts.size();
+    if (nsub == 0) return fail(SBR_ERR_NO_INTERACTIONS, "No interactions were supplied.");  // :86-88
+    if (nsub > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "too many sub-sequences");
+    std::lock_guard<std::mutex> lk(m->mu);
+    // :84 parameters.rng().shuffle(&mut subsequences)
+    std::vector<uint32_t> order(nsub);
+    for (size_t i = 0; i < nsub; ++i) order[i] = (uint32_t)i;
+    for (size_t i = nsub; i >= 2;) { i -= 1; const size_t j = (size_t)xs_gen_below(m->rng, (uint64_t)i + 1); std::swap(order[i], order[j]); }
+    // :90-98 partitions
+    size_t P = m->h.num_threads;
+    if (P == 0) {
+        const size_t autoP = (size_t)train_auto_partitions(m->dev, device_info().sms);
+        P = std::min(autoP, std::max<size_t>(1, nsub / 32));
+    }
+    if (P > nsub) return fail(SBR_ERR_INVALID_ARGUMENT, "num_threads exceeds the number of sub-sequences (the reference panics in chunks_mut(0))");
+    const size_t n = nsub / P;  // :91, remainder dropped by the zip at :94-96
+    std::vector<XorShift> rngs(P); std::vector<uint64_t> keys(P);
+    for (size_t p = 0; p < P; ++p) {  // :97 XorShiftRng::from_seed(parameters.rng().gen())
+        uint8_t seed[16];
+        for (int i = 0; i < 16; ++i) seed[i] = (uint8_t)xs_next_u32(m->rng);
+        xs_from_seed(rngs[p], seed);
+        uint64_t k = 0; for (int i = 0; i < 8; ++i) k |= (uint64_t)seed[i] << (8 * i);
+        keys[p] = k;
+    }
+    for (size_t i = 0; i < P * n; ++i) timesteps += lens[order[i]] - 1;
+    const double t1 = now_ms();
+
+    sbr_fit_plan* pl = new (std::nothrow) sbr_fit_plan();
+    if (!pl) return fail(SBR_ERR_INVALID_ARGUMENT, "out of memory");
+    pl->model = m; pl->nsub = nsub; pl->P = P; pl->n = n;
+    pl->timesteps_per_epoch = timesteps;
+    pl->stats.host_prepare_ms = t1 - t0;
+    cudaStream_t st = m->stream;
+    auto bail = [&](sbr_status r) { delete pl; return r; };
+#define CUP(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return bail(cuda_fail(e__, #expr)); } while (0)
+    for (cudaEvent_t* e : {&pl->ev0, &pl->ev1, &pl->evk0, &pl->evk1}) CUP(cudaEventCreate(e));
+    CUP(cudaEventRecord(pl->ev0, st));
+    s = ensure_uploaded(c, st);
+    if (s) return bail(s);
+    size_t h2d = c->upload_bytes;
+    PlanDev& d = pl->dev;
+    d.item_ids = c->d_item_ids;
+    CUP(cudaMalloc(&pl->d_seq_start, nsub * sizeof(uint64_t)));
+    CUP(cudaMalloc(&pl->d_seq_len, nsub * sizeof(uint32_t)));
+    CUP(cudaMalloc(&d.order, P * n * sizeof(uint32_t)));
+    CUP(cudaMalloc(&d.rng, P * sizeof(XorShift)));
+    CUP(cudaMalloc(&d.keys, P * sizeof(uint64_t)));
+    CUP(cudaMalloc(&d.step_ctr, P * sizeof(uint64_t)));
+    CUP(cudaMalloc(&d.loss_acc, P * sizeof(float)));
+    CUP(cudaMalloc(&d.examples, P * sizeof(unsigned long long)));
+    d.scratch_stride = train_scratch_floats_per_warp(m->dev);
+    CUP(cudaMalloc(&d.scratch, P * d.scratch_stride * sizeof(float)));
+    CUP(cudaMemcpyAsync(pl->d_seq_start, starts.data(), nsub * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUP(cudaMemcpyAsync(pl->d_seq_len, lens.data(), nsub * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CUP(cudaMemcpyAsync(d.order, order.data(), P * n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CUP(cudaMemcpyAsync(d.rng, rngs.data(), P * sizeof(XorShift), cudaMemcpyHostToDevice, st));
+    CUP(cudaMemcpyAsync(d.keys, keys.data(), P * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUP(cudaMemsetAsync(d.step_ctr, 0, P * sizeof(uint64_t), st));
+    CUP(cudaMemsetAsync(d.loss_acc, 0, P * sizeof(float), st));
+    CUP(cudaMemsetAsync(d.examples, 0, P * sizeof(unsigned long long), st));
+    CUP(cudaStreamSynchronize(st));  // host vectors go out of scope
+    h2d += nsub * 12 + P * n * 4 + P * (sizeof(XorShift) + 8);
+    d.seq_start = pl->d_seq_start; d.seq_len = pl->d_seq_len;
+    d.n = (uint32_t)n; d.P = (uint32_t)P;
+    d.neg_range = (uint32_t)c->num_items;  // :74 Uniform::new(0, interactions.num_items())
+    pl->stats.h2d_bytes = h2d;
+    pl->stats.partitions = P;
+#undef CUP
+    *out = pl;
+    return SBR_OK;
+}
+
+sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
+    if (!pl) return fail(SBR_ERR_INVALID_ARGUMENT, "null plan");
+    sbr_status s = require_device();
+    if (s) return s;
+    sbr_model* m = pl->model;
+    std::lock_guard<std::mutex> lk(m->mu);
+    cudaStream_t st = m->stream;
+    const size_t P = pl->P;
+    pl->dev.epochs = (int)m->h.num_epochs;
+    pl->dev.adam_t0 = m->num_updates;
+    CU(cudaMemsetAsync(pl->dev.loss_acc, 0, P * sizeof(float), st));
+    CU(cudaMemsetAsync(pl->dev.examples, 0, P * sizeof(unsigned long long), st));
+    int launches = 0;
+    CU(cudaEventRecord(pl->evk0, st));
+    if (pl->dev.epochs > 0) {
+        cudaError_t e;
+        launches = launch_train(m->dev, pl->dev, device_info().sms, st, &e);
+        if (e != cudaSuccess) return cuda_fail(e, "launch_train");
+    }
+    CU(cudaEventRecord(pl->evk1, st));
+    std::vector<float> loss(P); std::vector<unsigned long long> ex(P);
+    CU(cudaMemcpyAsync(loss.data(), pl->dev.loss_acc, P * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ex.data(), pl->dev.examples, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(pl->ev1, st));
+    CU(cudaStreamSynchronize(st));
+    float total = 0.0f; uint64_t tsteps = 0;
+    for (size_t p = 0; p < P; ++p) { total += loss[p] / (1.0f + (float)ex[p]); tsteps += ex[p]; }  // :173-175
+    const uint64_t steps = (uint64_t)P * pl->n * (uint64_t)pl->dev.epochs;
+    m->num_updates += steps;
+    float kms = 0.0f, tms = 0.0f;
+    CU(cudaEventElapsedTime(&kms, pl->evk0, pl->evk1));
+    CU(cudaEventElapsedTime(&tms, pl->ev0, pl->ev1));
+    pl->stats.steps = steps; pl->stats.timesteps = tsteps;
+    pl->stats.kernel_launches = (uint64_t)launches;
+    pl->stats.d2h_bytes = P * 12;
+    pl->stats.train_kernel_ms = kms; pl->stats.total_device_ms = tms;
+    if (loss_out) *loss_out = total;
+    return SBR_OK;
+}
+
+sbr_status sbr_fit_plan_stats(const sbr_fit_plan* p, sbr_fit_stats* out) {
+    if (!p || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = p->stats;
+    return SBR_OK;
+}
+void sbr_fit_plan_free(sbr_fit_plan* p) { if (p) { cudaSetDevice(g_device); delete p; } }
+
+sbr_status sbr_model_fit(sbr_model* m, const sbr_compressed* c, float* loss_out) {
+    sbr_fit_plan* pl = nullptr;
+    sbr_status s = sbr_fit_plan_create(m, c, &pl);
+    if (s) return s;
+    s = sbr_fit_plan_run(pl, loss_out);
+    if (s == SBR_OK) m->last = pl->stats;
+    sbr_fit_plan_free(pl);
+    return s;
+}
+
+sbr_status sbr_model_last_fit_stats(const sbr_model* m, sbr_fit_stats* out) {
+    if (!m || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = m->last;
+    return SBR_OK;
+}
+
+// --------------------------------------------------------------------------------------------- inference ----
+sbr_status sbr_model_user_representations(const sbr_model* m, const uint64_t* ptr, const uint64_t* item_ids, size_t num_users,
+                                          float* out) {
+    if (!m || !ptr || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    sbr_status s = require_device();
+    if (s) return s;
+    if (num_users == 0) return SBR_OK;
+    const size_t nnz = ptr[num_users];
+    if (nnz && !item_ids) return fail(SBR_ERR_INVALID_ARGUMENT, "null item_ids");
+    std::lock_guard<std::mutex> lk(m->mu);
+    cudaStream_t st = m->stream;
+    uint32_t* d_ids = nullptr; uint64_t* d_ptr = nullptr; float* d_out = nullptr;
+    const size_t D = m->dev.D;
+    CU(cudaMalloc(&d_ids, std::max<size_t>(nnz, 1) * sizeof(uint32_t)));
+    cudaError_t e = cudaMalloc(&d_ptr, (num_users + 1) * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, num_users * D * sizeof(float));
+    if (e == cudaSuccess) {
+        s = upload_ids_u32(item_ids, nnz, d_ids, st, m->dev.N, nullptr);
+        if (s == SBR_OK) {
+            e = cudaMemcpyAsync(d_ptr, ptr, (num_users + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = launch_user_representations(m->dev, d_ptr, d_ids, num_users, d_out, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, num_users * D * sizeof(float), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+    }
+    cudaFree(d_ids); cudaFree(d_ptr); cudaFree(d_out);
+    if (s) return s;
+    if (e != cudaSuccess) return cuda_fail(e, "user_representations");
+    return SBR_OK;
+}
+
+sbr_status sbr_model_user_representation(const sbr_model* m, const uint64_t* item_ids, size_t n, float* out) {
+    const uint64_t ptr[2] = {0, (uint64_t)n};
+    return sbr_model_user_representations(m, ptr, item_ids, 1, out);
+}
+
+sbr_status sbr_model_predict(const sbr_model* m, const float* user, const uint64_t* item_ids, size_t k, float* out) {
+    if (!m || !user || (k && (!item_ids || !out))) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    sbr_status s = require_device();
+    if (s) return s;
+    if (k == 0) return SBR_OK;
+    std::lock_guard<std::mutex> lk(m->mu);
+    cudaStream_t st = m->stream;
+    const size_t D = m->dev.D;
+    uint32_t* d_ids = nullptr; float* d_user = nullptr; float* d_out = nullptr; int* d_flag = nullptr;
+    CU(cudaMalloc(&d_ids, k * sizeof(uint32_t)));
+    cudaError_t e = cudaMalloc(&d_user, D * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, k * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_flag, sizeof(int));
+    int flag = 0;
+    if (e == cudaSuccess) {
+        s = upload_ids_u32(item_ids, k, d_ids, st, m->dev.N, nullptr);
+        if (s == SBR_OK) {
+            e = cudaMemcpyAsync(d_user, user, D * sizeof(float), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, sizeof(int), st);
+            if (e == cudaSuccess) e = launch_predict(m->dev, d_user, d_ids, k, d_out, d_flag, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, k * sizeof(float), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+    }
+    cudaFree(d_ids); cudaFree(d_user); cudaFree(d_out); cudaFree(d_flag);
+    if (s) return s;
+    if (e != cudaSuccess) return cuda_fail(e, "predict");
+    if (flag) return fail(SBR_ERR_INVALID_PREDICTION, "Invalid prediction value: non-finite or not a number.");
+    return SBR_OK;
+}
+
+sbr_status sbr_model_mrr_score(const sbr_model* m, const sbr_compressed* test, float* out) {
+    if (!m || !test || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    sbr_status s = require_device();
+    if (s) return s;
+    if (test->num_items > m->dev.N) return fail(SBR_ERR_INVALID_ARGUMENT, "test.num_items exceeds the model's num_items");
+    std::lock_guard<std::mutex> lk(m->mu);
+    cudaStream_t st = m->stream;
+    s = ensure_uploaded(test, st);
+    if (s) return s;
+    const size_t U = test->num_users;
+    std::vector<float> rr(U, 0.0f);
+    int flag = 0;
+    if (U && test->d_item_ids) {
+        float* d_rr = nullptr; int* d_flag = nullptr;
+        CU(cudaMalloc(&d_rr, U * sizeof(float)));
+        cudaError_t e = cudaMalloc(&d_flag, sizeof(int));
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, sizeof(int), st);
+        if (e == cudaSuccess) e = launch_mrr(m->dev, test->d_user_ptr, test->d_item_ids, U, d_rr, d_flag, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(rr.data(), d_rr, U * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(d_rr); cudaFree(d_flag);
+        if (e != cudaSuccess) return cuda_fail(e, "mrr_score");
+    }
+    if (flag) return fail(SBR_ERR_INVALID_PREDICTION, "Invalid prediction value: non-finite or not a number.");
+    float sum = 0.0f; size_t cnt = 0;  // evaluation.rs:47 mrrs.iter().sum::<f32>() / mrrs.len() as f32, user order
+    for (size_t u = 0; u < U; ++u)
+        if (test->user_ptr[u + 1] - test->user_ptr[u] >= 2) { sum += rr[u]; ++cnt; }
+    *out = cnt ? sum / (float)cnt : NAN;
+    return SBR_OK;
+}
+
+sbr_status sbr_model_gather_rows(const sbr_model* m, const uint64_t* item_ids, size_t n, float* out) {
+    if (!m || (n && (!item_ids || !out))) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    sbr_status s = require_device();
+    if (s) return s;
+    if (n == 0) return SBR_OK;
+    std::lock_guard<std::mutex> lk(m->mu);
+    cudaStream_t st = m->stream;
+    const size_t D = m->dev.D;
+    uint32_t* d_ids = nullptr; float* d_out = nullptr;
+    CU(cudaMalloc(&d_ids, n * sizeof(uint32_t)));
+    cudaError_t e = cudaMalloc(&d_out, n * D * sizeof(float));
+    if (e == cudaSuccess) {
+        s = upload_ids_u32(item_ids, n, d_ids, st, m->dev.N, nullptr);
+        if (s == SBR_OK) {
+            e = launch_gather_rows(m->dev, d_ids, n, d_out, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * D * sizeof(float), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+    }
+    cudaFree(d_ids); cudaFree(d_out);
+    if (s) return s;
+    if (e != cudaSuccess) return cuda_fail(e, "gather_rows");
+    return SBR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+// engine.h -- plain structs shared by the host driver (api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace sbr {
+
+enum { MODEL_LSTM = 0, MODEL_EWMA = 1 };
+
+// Device-resident model (HBM layout, see DESIGN.md "Data layout")
+struct ModelDev {
+    int model, variant, loss, opt;
+    uint32_t N;
+    int D, T;
+    int S;           // floats-vectors per item row record: 2 (w,G) Adagrad, 3 (w,m,v) Adam
+    float* E;        // [N][S][D]
+    float4* B;       // [N] {b, s1, s2, pad}
+    float* dense;    // [3][ndense]  w | s1 | s2  (LSTM: W[2D][4][D] then bias[4][D]; EWMA: alpha[D])
+    size_t ndense;
+    float lr, l2;
+};
+
+// Device-resident schedule of one fit(): sequence_model.rs:74-98 materialised in HBM
+struct PlanDev {
+    const uint32_t* item_ids;   // [nnz] narrowed item-id stream
+    const uint64_t* seq_start;  // [nsub] offset of each sub-sequence in item_ids
+    const uint32_t* seq_len;    // [nsub]
+    uint32_t* order;            // [P*n] partition-major indices into seq_*; shuffled in place every epoch
+    uint32_t n;                 // sub-sequences per partition (= nsub / P, remainder dropped)
+    uint32_t P;                 // partitions ("num_threads")
+    uint32_t neg_range;         // negatives ~ U[0, interactions.num_items)  (sequence_model.rs:74)
+    XorShift* rng;              // [P] per-partition shuffle rng (persists across runs)
+    uint64_t* keys;             // [P] negative-sampler keys
+    uint64_t* step_ctr;         // [P] optimizer steps done so far by each partition
+    float* loss_acc;            // [P] sum of sequence losses
+    unsigned long long* examples;  // [P] sum of timesteps
+    float* scratch;             // warp-private activations for backward
+    size_t scratch_stride;      // floats per warp
+    int epochs;
+    unsigned long long adam_t0; // model num_updates before this run
+};
+
+// launchers (kernels_train.cu / kernels_infer.cu); all enqueue on `st` and return the launch count
+int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t st, cudaError_t* err);
+size_t train_scratch_floats_per_warp(const ModelDev& m);
+int train_auto_partitions(const ModelDev& m, int num_sms);
+bool train_supported(const ModelDev& m, const char** why);
+
+cudaError_t launch_gather_rows(const ModelDev& m, const uint32_t* ids_dev, size_t n, float* out_dev, cudaStream_t st);
+cudaError_t launch_user_representations(const ModelDev& m, const uint64_t* ptr_dev, const uint32_t* ids_dev, size_t num_users,
+                                        float* out_dev, cudaStream_t st);
+cudaError_t launch_predict(const ModelDev& m, const float* user_dev, const uint32_t* ids_dev, size_t k, float* out_dev,
+                           int* nonfinite_dev, cudaStream_t st);
+// reciprocal rank per user with >= 2 interactions (0 for the others); evaluation.rs:12-48
+cudaError_t launch_mrr(const ModelDev& m, const uint64_t* ptr_dev, const uint32_t* ids_dev, size_t num_users, float* rr_dev,
+                       int* nonfinite_dev, cudaStream_t st);
+cudaError_t launch_init_embeddings(const ModelDev& m, uint64_t seed, cudaStream_t st);
+// strided copy between packed host-order blobs and the record layouts
+cudaError_t launch_pack_rows(const ModelDev& m, int slot, const float* packed_dev, cudaStream_t st);    // packed[N*D] -> E slot
+cudaError_t launch_unpack_rows(const ModelDev& m, int slot, float* packed_dev, cudaStream_t st);        // E slot -> packed
+cudaError_t launch_pack_bias(const ModelDev& m, int slot, const float* packed_dev, cudaStream_t st);
+cudaError_t launch_unpack_bias(const ModelDev& m, int slot, float* packed_dev, cudaStream_t st);
+
+}  // namespace sbr

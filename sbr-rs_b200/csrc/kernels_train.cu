@@ -1,0 +1,494 @@
+// kernels_train.cu -- Hogwild training kernels (one warp == one reference "thread" / partition).
+//
+// Replaces the rayon body of fit_sequence_model (sequence_model.rs:100-175) and the wyrm graph it drives
+// (lstm.rs:258-337, ewma.rs:266-352): for every sub-sequence of its partition a warp does gather -> recurrent
+// forward -> negative sampling / scoring -> backward -> sparse optimizer visits, with the parameters shared
+// lock-free in HBM/L2 exactly like Arc<HogwildParameter> (lstm.rs:175-181,259-260).  One launch runs all epochs.
+#include <cuda_runtime.h>
+
+#include "engine.h"
+
+namespace sbr {
+
+namespace {
+
+// In-place Fisher-Yates of one partition by lane 0 (thread_rng.shuffle(partition), sequence_model.rs:109)
+__device__ __forceinline__ void shuffle_partition(uint32_t* ord, uint32_t n, XorShift& rng) {
+    uint32_t i = n;
+    while (i >= 2) {
+        i -= 1;
+        uint32_t j = (uint32_t)xs_gen_below(rng, (uint64_t)i + 1);
+        uint32_t a = ord[i], b = ord[j];
+        ord[i] = b; ord[j] = a;
+    }
+}
+
+struct StepOut { float loss; float g; };
+
+__device__ __forceinline__ StepOut pair_loss(int loss_kind, float pos, float neg) {
+    StepOut r;
+    if (loss_kind == 0) {  // BPR: sigmoid(neg - pos)   lstm.rs:317
+        float s = sigmoidf_(neg - pos);
+        r.loss = s; r.g = s * (1.0f - s);
+    } else {               // Hinge / WARP: relu(1 + neg - pos)   lstm.rs:318
+        float v = 1.0f + neg - pos;
+        r.loss = v > 0.0f ? v : 0.0f; r.g = v > 0.0f ? 1.0f : 0.0f;
+    }
+    return r;
+}
+
+// Scores h against the target and draws the negative (uniform, or WARP rejection sampling,
+// sequence_model.rs:47-68): returns pos / neg scores, leaves the rows in p / q.
+template <int D>
+__device__ __forceinline__ void score_and_sample(const ModelDev& m, int lane, const float (&h)[VecOf<D>::V], uint32_t out,
+                                                 uint64_t key, uint64_t step, uint32_t t, uint32_t range, float (&p)[VecOf<D>::V],
+                                                 float (&q)[VecOf<D>::V], uint32_t& neg, float& pos, float& ngs) {
+    const size_t RS = (size_t)m.S * D;
+    row_load_cg<D>(m.E + (size_t)out * RS, lane, p);
+    pos = warp_dot<D>(h, p) + __ldcg(reinterpret_cast<const float*>(m.B + out));
+    const int tries = m.loss == 2 ? 5 : 1;
+    for (int j = 0; j < tries; ++j) {
+        neg = draw_item(key, step, t, (uint32_t)j, range);
+        row_load_cg<D>(m.E + (size_t)neg * RS, lane, q);
+        ngs = warp_dot<D>(h, q) + __ldcg(reinterpret_cast<const float*>(m.B + neg));
+        if (1.0f - pos + ngs > 0.0f) break;  // warp-uniform
+    }
+}
+
+// dense (non-embedding) parameter visit by one warp: element i of [w | s1 | s2] arrays of length nd
+template <int D>
+__device__ __forceinline__ void update_dense_vec(float* dense, size_t nd, size_t off, int lane, const float (&g)[VecOf<D>::V],
+                                                 const OptCfg& o) {
+    constexpr int V = VecOf<D>::V;
+    float w[V], s1[V], s2[V];
+    row_load_cg<D>(dense + off, lane, w);
+    row_load_cg<D>(dense + nd + off, lane, s1);
+    if (o.adam) row_load_cg<D>(dense + 2 * nd + off, lane, s2);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        if (o.adam) adam_elem(w[v], s1[v], s2[v], g[v], o);
+        else adagrad_elem(w[v], s1[v], g[v], o.lr, o.l2);
+    }
+    row_store_cg<D>(dense + off, lane, w);
+    row_store_cg<D>(dense + nd + off, lane, s1);
+    if (o.adam) row_store_cg<D>(dense + 2 * nd + off, lane, s2);
+}
+
+// =====================================================================================================
+// EWMA (ewma.rs:266-352): s_0 = x_0, s_t = a*s_{t-1} + (1-a)*x_t, a = sigmoid(alpha)
+// scratch per warp: S[T][D] X[T][D] DQ[T][D] G[T] NEG[T]
+// =====================================================================================================
+template <int D>
+__global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl) {
+    constexpr int V = VecOf<D>::V;
+    const int lane = threadIdx.x & 31;
+    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= pl.P) return;
+    const int T = m.T;
+    const size_t RS = (size_t)m.S * D;
+    float* ws = pl.scratch + (size_t)p * pl.scratch_stride;
+    float* S_ = ws; float* X_ = ws + (size_t)T * D; float* DQ = ws + 2 * (size_t)T * D;
+    float* G_ = ws + 3 * (size_t)T * D; uint32_t* NEG = reinterpret_cast<uint32_t*>(G_ + T);
+
+    XorShift rng = pl.rng[p];
+    const uint64_t key = pl.keys[p];
+    uint64_t step = pl.step_ctr[p];
+    uint32_t* ord = pl.order + (size_t)p * pl.n;
+    float loss_acc = 0.0f; unsigned long long ex = 0;
+    OptCfg o; o.lr = m.lr; o.l2 = m.l2; o.adam = m.opt == 1; o.c1 = 1.0f; o.c2 = 1.0f;
+
+    for (int ep = 0; ep < pl.epochs; ++ep) {
+        if (lane == 0) shuffle_partition(ord, pl.n, rng);
+        __syncwarp();
+        for (uint32_t i = 0; i < pl.n; ++i, ++step) {
+            const uint32_t sq = ord[i];
+            const uint32_t* ids = pl.item_ids + pl.seq_start[sq];
+            const int Tn = (int)pl.seq_len[sq] - 1;
+            adam_corrections(o, pl.adam_t0 + step * pl.P + p + 1);
+
+            float al[V], a[V], s[V];
+            row_load_cg<D>(m.dense, lane, al);
+#pragma unroll
+            for (int v = 0; v < V; ++v) { a[v] = sigmoidf_(al[v]); s[v] = 0.0f; }
+
+            float loss_seq = 0.0f;
+            // ---- forward ----
+            for (int t = 0; t < Tn; ++t) {
+                const uint32_t in = __ldg(ids + t), out = __ldg(ids + t + 1);
+                float x[V], pv[V], qv[V];
+                row_load_cg<D>(m.E + (size_t)in * RS, lane, x);  // item_embeddings.index(input)
+#pragma unroll
+                for (int v = 0; v < V; ++v) s[v] = t == 0 ? x[v] : a[v] * s[v] + (1.0f - a[v]) * x[v];
+                vec_store<D>(S_ + (size_t)t * D, lane, s);
+                vec_store<D>(X_ + (size_t)t * D, lane, x);
+                uint32_t neg; float pos, ngs;
+                score_and_sample<D>(m, lane, s, out, key, step, (uint32_t)t, pl.neg_range, pv, qv, neg, pos, ngs);
+                StepOut lo = pair_loss(m.loss, pos, ngs);
+                loss_seq += lo.loss;
+                float dq[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) dq[v] = lo.g * (qv[v] - pv[v]);
+                vec_store<D>(DQ + (size_t)t * D, lane, dq);
+                if (lane == 0) { G_[t] = lo.g; NEG[t] = neg; }
+            }
+            __syncwarp();
+            // ---- backward + sparse optimizer visits (t descending: E[neg], E[out], E[in]) ----
+            float ds[V], da[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) { ds[v] = 0.0f; da[v] = 0.0f; }
+            for (int t = Tn - 1; t >= 0; --t) {
+                const uint32_t in = __ldg(ids + t), out = __ldg(ids + t + 1);
+                const uint32_t neg = NEG[t]; const float g = G_[t];
+                float st[V], dq[V], dh[V], dx[V], gn[V], gp[V];
+                vec_load<D>(S_ + (size_t)t * D, lane, st);
+                vec_load<D>(DQ + (size_t)t * D, lane, dq);
+#pragma unroll
+                for (int v = 0; v < V; ++v) dh[v] = ds[v] + dq[v];
+                if (t == 0) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) { dx[v] = dh[v]; ds[v] = 0.0f; }
+                } else {
+                    float sp[V], x[V];
+                    vec_load<D>(S_ + (size_t)(t - 1) * D, lane, sp);
+                    vec_load<D>(X_ + (size_t)t * D, lane, x);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        dx[v] = (1.0f - a[v]) * dh[v];
+                        da[v] += dh[v] * (sp[v] - x[v]);
+                        ds[v] = a[v] * dh[v];
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < V; ++v) { gn[v] = g * st[v]; gp[v] = -g * st[v]; }
+                update_row<D>(m.E + (size_t)neg * RS, lane, gn, o);
+                update_row<D>(m.E + (size_t)out * RS, lane, gp, o);
+                update_row<D>(m.E + (size_t)in * RS, lane, dx, o);
+                if (lane == 0) {
+                    update_bias(m.B + neg, g, o);
+                    update_bias(m.B + out, -g, o);
+                }
+                __syncwarp();
+            }
+            // ---- dense: alpha ----
+            float dal[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) dal[v] = da[v] * a[v] * (1.0f - a[v]);
+            update_dense_vec<D>(m.dense, m.ndense, 0, lane, dal, o);
+            loss_acc += loss_seq; ex += (unsigned long long)Tn;
+        }
+    }
+    if (lane == 0) {
+        pl.rng[p] = rng; pl.step_ctr[p] = step;
+        pl.loss_acc[p] += loss_acc; pl.examples[p] += ex;
+    }
+}
+
+// =====================================================================================================
+// LSTM, FFMA path, D in {16, 32} (lstm.rs:258-337 + wyrm::nn::lstm).  Weights live in shared memory as
+// Ws[k][d] = float4{f,i,g,o}; the CTA's warps step in lock-step rounds: after each round the CTA-summed dense
+// gradient is applied to the global weights (Hogwild across CTAs) and the shared copy is refreshed.
+// With num_threads == 1 this is exactly the reference's one-dense-step-per-sequence order.
+// scratch per warp: [T][8][D] = x,h,c,f,i,g,o,dq ; then G[T], NEG[T]
+// =====================================================================================================
+template <int NV>
+__device__ __forceinline__ void warp_multi_reduce(float (&v)[NV], int lane) {
+    // Reduces NV independent sums across the 32 lanes with NV-NV/32 shuffles; afterwards lane L holds, in
+    // v[0..NV/32), the complete sums of the slots that were stored at positions (NV/32)*L + i.
+    int n = NV;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const int half = n >> 1;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < NV / 2; ++i) {
+            if (i < half) {
+                float keep = up ? v[i + half] : v[i];
+                float send = up ? v[i] : v[i + half];
+                v[i] = keep + __shfl_xor_sync(kFull, send, off);
+            }
+        }
+        n = half;
+    }
+}
+
+template <int D, int WPC>
+__global__ void __launch_bounds__(WPC * 32) lstm_train_kernel(ModelDev m, PlanDev pl) {
+    static_assert(D == 16 || D == 32, "FFMA LSTM path supports D in {16, 32}");
+    constexpr int NK = 2 * D;       // rows of W: [h ; x]
+    constexpr int R = NK / 32;      // sums per lane after the multi-reduce
+    extern __shared__ float4 smem4[];
+    float4* Ws = smem4;                       // [NK][D]
+    float4* dWs = Ws + NK * D;                // [NK][D]
+    float4* Bs = dWs + NK * D;                // [D]
+    float4* dBs = Bs + D;                     // [D]
+    float* zbuf = reinterpret_cast<float*>(dBs + D);  // [WPC][NK]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool act = lane < D;
+    const int ld = act ? lane : 0;
+    const uint32_t p = blockIdx.x * WPC + warp;
+    const bool live = p < pl.P;
+    const int T = m.T;
+    const size_t RS = (size_t)m.S * D;
+    const size_t nd = m.ndense;
+    const bool coupled = m.variant == 1;
+    float* myz = zbuf + warp * NK;
+    float* ws = pl.scratch + (size_t)(live ? p : 0) * pl.scratch_stride;
+    float* G_ = ws + (size_t)T * 8 * D; uint32_t* NEG = reinterpret_cast<uint32_t*>(G_ + T);
+    auto slot = [&](int t, int which) { return ws + ((size_t)t * 8 + which) * D; };
+    enum { SX = 0, SH = 1, SC = 2, SF = 3, SI = 4, SG = 5, SO = 6, SDQ = 7 };
+
+    // stage weights: global canonical W[k][q][d], B[q][d]
+    for (int idx = threadIdx.x; idx < NK * D; idx += WPC * 32) {
+        const int k = idx / D, d = idx % D;
+        const float* src = m.dense + (size_t)k * 4 * D + d;
+        Ws[idx] = make_float4(__ldcg(src), __ldcg(src + D), __ldcg(src + 2 * D), __ldcg(src + 3 * D));
+        dWs[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int d = threadIdx.x; d < D; d += WPC * 32) {
+        const float* src = m.dense + (size_t)NK * 4 * D + d;
+        Bs[d] = make_float4(__ldcg(src), __ldcg(src + D), __ldcg(src + 2 * D), __ldcg(src + 3 * D));
+        dBs[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+
+    XorShift rng; uint64_t key = 0; uint32_t* ord = nullptr;
+    uint64_t step = pl.step_ctr[live ? p : 0];  // all partitions have done the same number of steps
+    if (live) { rng = pl.rng[p]; key = pl.keys[p]; ord = pl.order + (size_t)p * pl.n; }
+    float loss_acc = 0.0f; unsigned long long ex = 0;
+    OptCfg o; o.lr = m.lr; o.l2 = m.l2; o.adam = m.opt == 1; o.c1 = 1.0f; o.c2 = 1.0f;
+
+    for (int ep = 0; ep < pl.epochs; ++ep) {
+        if (live && lane == 0) shuffle_partition(ord, pl.n, rng);
+        __syncwarp();
+        for (uint32_t i = 0; i < pl.n; ++i, ++step) {
+            adam_corrections(o, pl.adam_t0 + step * pl.P + (live ? p : blockIdx.x * WPC) + 1);
+            if (live) {
+                const uint32_t sq = ord[i];
+                const uint32_t* ids = pl.item_ids + pl.seq_start[sq];
+                const int Tn = (int)pl.seq_len[sq] - 1;
+                float h = 0.0f, c = 0.0f, loss_seq = 0.0f;
+                // ---------------- forward ----------------
+                for (int t = 0; t < Tn; ++t) {
+                    const uint32_t in = __ldg(ids + t), out = __ldg(ids + t + 1);
+                    float x[1], hv[1], pv[1], qv[1];
+                    row_load_cg<D>(m.E + (size_t)in * RS, lane, x);
+                    if (act) { myz[lane] = h; myz[D + lane] = x[0]; }
+                    __syncwarp();
+                    float4 pre = Bs[ld];
+#pragma unroll 4
+                    for (int k4 = 0; k4 < NK / 4; ++k4) {
+                        const float4 z4 = reinterpret_cast<const float4*>(myz)[k4];
+                        const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const float4 w4 = Ws[(k4 * 4 + kk) * D + ld];
+                            pre.x = fmaf(zz[kk], w4.x, pre.x); pre.y = fmaf(zz[kk], w4.y, pre.y);
+                            pre.z = fmaf(zz[kk], w4.z, pre.z); pre.w = fmaf(zz[kk], w4.w, pre.w);
+                        }
+                    }
+                    __syncwarp();
+                    const float f = sigmoidf_(pre.x);
+                    const float ig = coupled ? 1.0f - f : sigmoidf_(pre.y);
+                    const float gg = tanhf(pre.z);
+                    const float og = sigmoidf_(pre.w);
+                    const float cn = f * c + ig * gg;
+                    const float tc = tanhf(cn);
+                    c = act ? cn : 0.0f;
+                    h = act ? og * tc : 0.0f;
+                    if (act) {
+                        slot(t, SX)[lane] = x[0]; slot(t, SH)[lane] = h; slot(t, SC)[lane] = c;
+                        slot(t, SF)[lane] = f; slot(t, SI)[lane] = ig; slot(t, SG)[lane] = gg; slot(t, SO)[lane] = og;
+                    }
+                    hv[0] = h;
+                    uint32_t neg; float pos, ngs;
+                    score_and_sample<D>(m, lane, hv, out, key, step, (uint32_t)t, pl.neg_range, pv, qv, neg, pos, ngs);
+                    StepOut lo = pair_loss(m.loss, pos, ngs);
+                    loss_seq += lo.loss;
+                    if (act) slot(t, SDQ)[lane] = lo.g * (qv[0] - pv[0]);
+                    if (lane == 0) { G_[t] = lo.g; NEG[t] = neg; }
+                }
+                __syncwarp();
+                // ---------------- backward ----------------
+                float dh_rec = 0.0f, dc_rec = 0.0f;
+                float4 db = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int t = Tn - 1; t >= 0; --t) {
+                    const uint32_t in = __ldg(ids + t), out = __ldg(ids + t + 1);
+                    const uint32_t neg = NEG[t]; const float g = G_[t];
+                    float ht = 0.f, f = 0.f, ig = 0.f, gg = 0.f, og = 0.f, ct = 0.f, cp = 0.f, dq = 0.f;
+                    if (act) {
+                        ht = slot(t, SH)[lane]; ct = slot(t, SC)[lane]; f = slot(t, SF)[lane]; ig = slot(t, SI)[lane];
+                        gg = slot(t, SG)[lane]; og = slot(t, SO)[lane]; dq = slot(t, SDQ)[lane];
+                        cp = t ? slot(t - 1, SC)[lane] : 0.0f;
+                    }
+                    const float tc = tanhf(ct);
+                    const float dh = dh_rec + dq;
+                    const float d_o = dh * tc;
+                    const float dc = dc_rec + dh * og * (1.0f - tc * tc);
+                    float d_f = dc * cp, d_i = dc * gg;
+                    const float d_g = dc * ig;
+                    dc_rec = dc * f;
+                    if (coupled) { d_f -= d_i; d_i = 0.0f; }
+                    float4 del;
+                    del.x = d_f * f * (1.0f - f);
+                    del.y = coupled ? 0.0f : d_i * ig * (1.0f - ig);
+                    del.z = d_g * (1.0f - gg * gg);
+                    del.w = d_o * og * (1.0f - og);
+                    if (!act) del = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (act) {  // deltas replace the gates (consumed by the dW pass below)
+                        slot(t, SF)[lane] = del.x; slot(t, SI)[lane] = del.y; slot(t, SG)[lane] = del.z; slot(t, SO)[lane] = del.w;
+                    }
+                    db.x += del.x; db.y += del.y; db.z += del.z; db.w += del.w;
+                    // dz[k] = sum_{q,d} del[q][d] W[k][q][d]: lane-partials then a 32-lane multi-reduce
+                    float part[NK];
+#pragma unroll
+                    for (int k = 0; k < NK; ++k) {
+                        const float4 w4 = Ws[k * D + ld];
+                        float a0 = del.x * w4.x;
+                        a0 = fmaf(del.y, w4.y, a0); a0 = fmaf(del.z, w4.z, a0); a0 = fmaf(del.w, w4.w, a0);
+                        part[R * (k % 32) + k / 32] = a0;
+                    }
+                    warp_multi_reduce<NK>(part, lane);
+                    float dx;
+                    if constexpr (D == 32) { dh_rec = part[0]; dx = part[1]; }
+                    else { dx = __shfl_sync(kFull, part[0], (lane + 16) & 31); dh_rec = act ? part[0] : 0.0f; }
+                    float gn[1] = {g * ht}, gp[1] = {-g * ht}, gx[1] = {dx};
+                    update_row<D>(m.E + (size_t)neg * RS, lane, gn, o);
+                    update_row<D>(m.E + (size_t)out * RS, lane, gp, o);
+                    update_row<D>(m.E + (size_t)in * RS, lane, gx, o);
+                    if (lane == 0) {
+                        update_bias(m.B + neg, g, o);
+                        update_bias(m.B + out, -g, o);
+                    }
+                    __syncwarp();
+                }
+                // ---------------- dW = sum_t z_t^T delta_t, 8 rows of W at a time ----------------
+                if (act) {
+                    atomicAdd(&dBs[lane].x, db.x); atomicAdd(&dBs[lane].y, db.y);
+                    atomicAdd(&dBs[lane].z, db.z); atomicAdd(&dBs[lane].w, db.w);
+                }
+                for (int kc = 0; kc < NK / 8; ++kc) {
+                    float acc[8][4];
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) { acc[kk][0] = acc[kk][1] = acc[kk][2] = acc[kk][3] = 0.0f; }
+                    const bool hpart = kc * 8 < D;
+                    const int off = hpart ? kc * 8 : kc * 8 - D;
+                    for (int t = Tn - 1; t >= 0; --t) {
+                        float4 z0, z1;
+                        if (hpart && t == 0) { z0 = make_float4(0.f, 0.f, 0.f, 0.f); z1 = z0; }
+                        else {
+                            const float* zs = (hpart ? slot(t - 1, SH) : slot(t, SX)) + off;
+                            z0 = *reinterpret_cast<const float4*>(zs); z1 = *reinterpret_cast<const float4*>(zs + 4);
+                        }
+                        const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+                        float dl[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (act) { dl[0] = slot(t, SF)[lane]; dl[1] = slot(t, SI)[lane]; dl[2] = slot(t, SG)[lane]; dl[3] = slot(t, SO)[lane]; }
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) acc[kk][q] = fmaf(zz[kk], dl[q], acc[kk][q]);
+                    }
+                    if (act) {
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            float4* dst = &dWs[(kc * 8 + kk) * D + lane];
+                            atomicAdd(&dst->x, acc[kk][0]); atomicAdd(&dst->y, acc[kk][1]);
+                            atomicAdd(&dst->z, acc[kk][2]); atomicAdd(&dst->w, acc[kk][3]);
+                        }
+                    }
+                }
+                loss_acc += loss_seq; ex += (unsigned long long)Tn;
+            }
+            // ---------------- CTA round: dense optimizer step on the CTA-summed gradient ----------------
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < (int)nd; idx += WPC * 32) {
+                float gsum; float* sw; float* sdw;
+                if (idx < NK * 4 * D) {
+                    const int k = idx / (4 * D), q = (idx / D) % 4, d = idx % D;
+                    sw = reinterpret_cast<float*>(&Ws[k * D + d]) + q; sdw = reinterpret_cast<float*>(&dWs[k * D + d]) + q;
+                } else {
+                    const int j = idx - NK * 4 * D, q = j / D, d = j % D;
+                    sw = reinterpret_cast<float*>(&Bs[d]) + q; sdw = reinterpret_cast<float*>(&dBs[d]) + q;
+                }
+                gsum = *sdw; *sdw = 0.0f;
+                float w = __ldcg(m.dense + idx), s1 = __ldcg(m.dense + nd + idx);
+                if (o.adam) {
+                    float s2 = __ldcg(m.dense + 2 * nd + idx);
+                    adam_elem(w, s1, s2, gsum, o);
+                    __stcg(m.dense + 2 * nd + idx, s2);
+                } else adagrad_elem(w, s1, gsum, o.lr, o.l2);
+                __stcg(m.dense + idx, w); __stcg(m.dense + nd + idx, s1);
+                *sw = w;
+            }
+            __syncthreads();
+        }
+    }
+    if (live && lane == 0) {
+        pl.rng[p] = rng; pl.step_ctr[p] = step;
+        pl.loss_acc[p] += loss_acc; pl.examples[p] += ex;
+    }
+}
+
+template <int D, int WPC>
+constexpr size_t lstm_smem_bytes() { return sizeof(float4) * (2 * (2 * D) * D + 2 * D) + sizeof(float) * WPC * 2 * D; }
+
+constexpr int kLstmWPC = 8;
+constexpr int kEwmaWPC = 8;
+
+}  // namespace
+
+bool train_supported(const ModelDev& m, const char** why) {
+    if (m.model == MODEL_EWMA) {
+        if (m.D == 16 || m.D == 32 || m.D == 64 || m.D == 128 || m.D == 256) return true;
+        *why = "EWMA embedding_dim must be one of 16, 32, 64, 128, 256";
+        return false;
+    }
+    if (m.D == 16 || m.D == 32) return true;
+    *why = "LSTM embedding_dim must be 16 or 32 on the FFMA path (larger dims: tensor-core path, not built yet)";
+    return false;
+}
+
+size_t train_scratch_floats_per_warp(const ModelDev& m) {
+    size_t T = (size_t)m.T, D = (size_t)m.D;
+    size_t n = (m.model == MODEL_EWMA ? 3 * T * D : 8 * T * D) + 2 * T;
+    return (n + 31) / 32 * 32;  // keep every warp's block 128-byte aligned
+}
+
+int train_auto_partitions(const ModelDev& m, int num_sms) {
+    // resident warps per SM the kernels reach (registers / shared memory), see DESIGN.md
+    int per_sm = m.model == MODEL_EWMA ? (m.D <= 64 ? 32 : 16) : 16;
+    return num_sms * per_sm;
+}
+
+int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t st, cudaError_t* err) {
+    (void)num_sms;
+    *err = cudaSuccess;
+    if (m.model == MODEL_EWMA) {
+        dim3 block(kEwmaWPC * 32), grid((p.P + kEwmaWPC - 1) / kEwmaWPC);
+        switch (m.D) {
+            case 16: ewma_train_kernel<16><<<grid, block, 0, st>>>(m, p); break;
+            case 32: ewma_train_kernel<32><<<grid, block, 0, st>>>(m, p); break;
+            case 64: ewma_train_kernel<64><<<grid, block, 0, st>>>(m, p); break;
+            case 128: ewma_train_kernel<128><<<grid, block, 0, st>>>(m, p); break;
+            case 256: ewma_train_kernel<256><<<grid, block, 0, st>>>(m, p); break;
+            default: *err = cudaErrorInvalidValue; return 0;
+        }
+    } else {
+        dim3 block(kLstmWPC * 32), grid((p.P + kLstmWPC - 1) / kLstmWPC);
+        if (m.D == 32) {
+            constexpr size_t smem = lstm_smem_bytes<32, kLstmWPC>();
+            *err = cudaFuncSetAttribute(lstm_train_kernel<32, kLstmWPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (*err != cudaSuccess) return 0;
+            lstm_train_kernel<32, kLstmWPC><<<grid, block, smem, st>>>(m, p);
+        } else if (m.D == 16) {
+            constexpr size_t smem = lstm_smem_bytes<16, kLstmWPC>();
+            *err = cudaFuncSetAttribute(lstm_train_kernel<16, kLstmWPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (*err != cudaSuccess) return 0;
+            lstm_train_kernel<16, kLstmWPC><<<grid, block, smem, st>>>(m, p);
+        } else { *err = cudaErrorInvalidValue; return 0; }
+    }
+    *err = cudaGetLastError();
+    return 1;
+}
+
+}  // namespace sbr

@@ -1,0 +1,198 @@
+"""Parity tests proper: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+
+Bar (north_star): bit-exact for the item-index gather and all integer work (sub-sequence schedule, shuffles,
+negative draws -- a wrong draw shows up as O(lr) parameter differences); fp32 tolerance elsewhere.
+Stated fp32 tolerance: after a fit with num_threads=1 (same update order as the reference's single thread) every
+parameter and optimizer-state element agrees with the oracle to |diff| <= 2e-4 (short runs) / 2e-3 (hundreds of
+steps); the sources are libm vs CUDA expf/tanhf (<= 2 ulp) and dot-product reduction order.
+"""
+import numpy as np
+import pytest
+
+from helpers import make_pair, max_abs_diff, random_csr, state_names, stream_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gather_bit_exact(pkg):
+    """ParameterNode::index (lstm.rs:272-283) is an exact copy: compare raw bits."""
+    for D in (16, 32, 64, 128, 256):
+        N = 5000
+        m = pkg.ewma.Hyperparameters(N, 8).embedding_dim(D).optimizer(pkg.Optimizer.Adagrad).from_seed(bytes(16)).build()
+        table = m.get_parameter("item_embeddings").reshape(N, D)
+        rng = np.random.default_rng(D)
+        for n in (0, 1, 31, 4097):
+            ids = rng.integers(0, N, size=n).astype(np.uint64)
+            if n >= 31:
+                ids[:3] = [0, N - 1, N - 1]  # edges + duplicate
+            out = m.gather_rows(ids)
+            assert out.shape == (n, D)
+            assert np.array_equal(out.view(np.uint32), table[ids.astype(np.int64)].view(np.uint32))
+        with pytest.raises(pkg.SbrError):
+            m.gather_rows(np.array([N], dtype=np.uint64))
+
+
+def test_init_statistics(pkg):
+    """embedding_init: N(0, (1/D)^2), biases 0, alpha 0 (lstm.rs:22-25,181; ewma.rs:175-178)."""
+    m = pkg.ewma.Hyperparameters(20000, 8).embedding_dim(32).from_seed(bytes(range(16))).build()
+    e = m.get_parameter("item_embeddings")
+    assert abs(e.mean()) < 2e-4 and abs(e.std() - 1.0 / 32) < 5e-4
+    assert not m.get_parameter("item_biases").any() and not m.get_parameter("alpha").any()
+    m2 = pkg.lstm.Hyperparameters(100, 8).embedding_dim(32).from_seed(bytes(range(16))).build()
+    w = m2.get_parameter("lstm_weights")
+    a = 1.0 / np.sqrt(32)
+    assert w.min() >= -a and w.max() <= a and abs(w.std() - a / np.sqrt(3)) < 5e-3
+
+
+CASES = [
+    # kind, D, loss, optimizer, variant
+    ("ewma", 32, "bpr", "adagrad", "normal"),
+    ("ewma", 32, "hinge", "adam", "normal"),
+    ("ewma", 32, "warp", "adagrad", "normal"),
+    ("ewma", 16, "bpr", "adam", "normal"),
+    ("ewma", 64, "warp", "adagrad", "normal"),
+    ("ewma", 128, "bpr", "adagrad", "normal"),
+    ("ewma", 256, "hinge", "adam", "normal"),
+    ("lstm", 32, "bpr", "adagrad", "normal"),
+    ("lstm", 32, "hinge", "adagrad", "coupled"),
+    ("lstm", 32, "warp", "adagrad", "normal"),
+    ("lstm", 32, "bpr", "adam", "coupled"),
+    ("lstm", 16, "warp", "adam", "normal"),
+    ("lstm", 16, "hinge", "adagrad", "coupled"),
+]
+
+
+@pytest.mark.parametrize("kind,D,loss,optimizer,variant", CASES)
+def test_fit_matches_oracle_single_thread(pkg, oracle, kind, D, loss, optimizer, variant):
+    """num_threads=1: one warp walks the shuffled sub-sequences in the reference's order
+    (sequence_model.rs:84,108-169); parameters AND optimizer state must match the oracle."""
+    rng = np.random.default_rng(7)
+    N, T = 300, 12
+    ptr, ids = random_csr(rng, 30, N, 1, 40)  # ragged: lengths 1..40 => dropped (<=2), short and full chunks
+    gm, om = make_pair(pkg, oracle, kind, N, T, D, loss=loss, optimizer=optimizer, variant=variant, lr=0.05, l2=1e-3,
+                       epochs=2, threads=1, scale=0.3)
+    data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
+    gl = gm.fit(data)
+    rc, ol = om.fit(ptr, ids)
+    assert rc == 0
+    diffs = max_abs_diff(gm, om, state_names(om, optimizer))
+    assert max(diffs.values()) <= 2e-4, diffs
+    assert abs(gl - ol) <= 1e-4 * max(1.0, abs(ol)), (gl, ol)
+    assert gm.num_updates == om.num_updates
+    assert gm.rng_state == om.rng_state  # master rng consumed identically (shuffle + per-partition seeds)
+    st = gm.last_fit_stats()
+    stt, ln = oracle.subsequences(ptr, T)
+    assert st["steps"] == 2 * len(stt) and st["timesteps"] == 2 * int((ln - 1).sum())
+
+
+def test_warm_restart_and_second_fit(pkg, oracle):
+    """State lives in the model across fit() calls (benches/benchmark.rs:40-42 relies on repeated fit)."""
+    rng = np.random.default_rng(11)
+    N, T, D = 200, 8, 32
+    ptr, ids = random_csr(rng, 20, N, 3, 30)
+    gm, om = make_pair(pkg, oracle, "ewma", N, T, D, loss="bpr", optimizer="adam", epochs=1, scale=0.3)
+    data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
+    for _ in range(3):
+        gm.fit(data)
+        assert om.fit(ptr, ids)[0] == 0
+    diffs = max_abs_diff(gm, om, state_names(om, "adam"))
+    assert max(diffs.values()) <= 5e-4, diffs
+
+
+@pytest.mark.parametrize("kind", ["ewma", "lstm"])
+def test_ml100k_shaped_epoch_single_thread(pkg, oracle, kind, ml100k):
+    """One epoch over real ML-100K sequences (first 150 users), seq 32 / dim 32 / WARP / Adagrad: config C1/C2."""
+    nu = 150
+    ptr = ml100k["user_ptr"][: nu + 1].astype(np.uint64)
+    ids = ml100k["item_ids"][: int(ptr[-1])].astype(np.uint64)
+    N = int(ml100k["num_items"])
+    gm, om = make_pair(pkg, oracle, kind, N, 32, 32, loss="warp", optimizer="adagrad", variant="normal", lr=0.16,
+                       l2=4e-4, epochs=1, threads=1)
+    data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
+    gl = gm.fit(data)
+    rc, ol = om.fit(ptr, ids)
+    assert rc == 0
+    diffs = max_abs_diff(gm, om, state_names(om, "adagrad"))
+    assert max(diffs.values()) <= 2e-3, diffs
+    assert abs(gl - ol) <= 2e-3 * max(1.0, abs(ol))
+
+
+def test_inference_matches_oracle(pkg, oracle):
+    """user_representation / predict / mrr_score (sequence_model.rs:180-233, evaluation.rs:12-48)."""
+    rng = np.random.default_rng(3)
+    N, T = 500, 16
+    for kind, D in (("lstm", 32), ("lstm", 16), ("ewma", 32), ("ewma", 128)):
+        gm, om = make_pair(pkg, oracle, kind, N, T, D, scale=0.3)
+        for n in (0, 1, 5, 16, 40):  # empty, shorter than T, exactly T, longer than T (last T used)
+            hist = rng.integers(0, N, size=n).astype(np.uint64)
+            u = gm.user_representation(hist)
+            rc, ou = om.user_representation(hist)
+            assert rc == 0
+            assert np.max(np.abs(u.user_embedding - ou)) <= 1e-5
+            items = rng.integers(0, N, size=77).astype(np.uint64)
+            p = gm.predict(u, items)
+            rc, op = om.predict(ou, items)
+            assert rc == 0 and np.max(np.abs(p - op)) <= 1e-5
+        ptr, ids = random_csr(rng, 60, N, 0, 40, first_item=0)
+        test = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
+        g_mrr = pkg.mrr_score(gm, test)
+        rc, o_mrr = om.mrr_score(ptr, ids)
+        assert rc == 0 and abs(g_mrr - o_mrr) <= 1e-4, (g_mrr, o_mrr)
+        with pytest.raises(pkg.SbrError):
+            gm.predict(u, np.array([N], dtype=np.uint64))
+
+
+def test_error_paths(pkg):
+    """lstm.rs:522-530 empty_interactions => NoInteractions; non-finite predictions => InvalidPredictionValue."""
+    data = pkg.Interactions(100, 100).to_compressed()
+    model = pkg.lstm.Hyperparameters(100, 100).embedding_dim(32).build()
+    with pytest.raises(pkg.NoInteractions):
+        model.fit(data)
+    # all sub-sequences of length <= 2 are dropped (sequence_model.rs:81) => also NoInteractions
+    ptr = np.array([0, 2, 4], dtype=np.uint64)
+    short = pkg.CompressedInteractions.from_csr(ptr, np.array([1, 2, 3, 4], dtype=np.uint64), None, num_items=100)
+    with pytest.raises(pkg.NoInteractions):
+        model.fit(short)
+    m = pkg.ewma.Hyperparameters(10, 4).embedding_dim(32).build()
+    e = m.get_parameter("item_embeddings")
+    e[32 * 3] = np.nan
+    m.set_parameter("item_embeddings", e)
+    u = pkg.ImplicitUser(np.ones(32, dtype=np.float32))
+    assert np.all(np.isfinite(m.predict(u, np.array([0, 1, 2], dtype=np.uint64))))
+    with pytest.raises(pkg.InvalidPredictionValue):
+        m.predict(u, np.array([0, 3], dtype=np.uint64))
+    # more partitions than sub-sequences: the reference panics in chunks_mut(0) (sequence_model.rs:91-95)
+    ptr = np.array([0, 5], dtype=np.uint64)
+    one = pkg.CompressedInteractions.from_csr(ptr, np.arange(5, dtype=np.uint64), None, num_items=10)
+    m2 = pkg.ewma.Hyperparameters(10, 8).embedding_dim(32).num_threads(4).build()
+    with pytest.raises(pkg.SbrError):
+        m2.fit(one)
+
+
+@pytest.mark.parametrize("kind", ["ewma", "lstm"])
+def test_hogwild_many_partitions_statistics(pkg, oracle, kind):
+    """num_threads >> 1 is lock-free Hogwild (Parallelism::Asynchronous, mod.rs:37-38): not bit-reproducible, so
+    parity is statistical -- the loss after the same number of epochs must match the oracle's single-thread run on
+    the same stream, and parameters must stay finite."""
+    rng = np.random.default_rng(5)
+    N, T, D = 1683, 32, 32
+    ptr, ids = stream_csr(rng, 4096, N, 32, zipf=True)
+    gm, om = make_pair(pkg, oracle, kind, N, T, D, loss="bpr", optimizer="adagrad", variant="normal", lr=0.05, l2=0.0,
+                       epochs=1, threads=64)
+    data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
+    l1 = gm.fit(data) / 64  # sum over partitions of per-partition means (sequence_model.rs:173-175)
+    l2_ = gm.fit(data) / 64
+    om.h.num_threads = 1
+    import ctypes as C
+    om1 = oracle.OracleModel(kind, N, T, embedding_dim=D, learning_rate=0.05, l2_penalty=0.0, lstm_variant="normal",
+                             loss="bpr", optimizer="adagrad", num_epochs=1, num_threads=1, seed=bytes(range(1, 17)))
+    for name in om1.param_names():
+        om1.param(name)[:] = om.param(name)
+    o1 = om1.fit(ptr, ids)[1]
+    o2 = om1.fit(ptr, ids)[1]
+    assert l2_ < l1 and o2 < o1                      # both learn
+    assert abs(l1 - o1) < 0.02 and abs(l2_ - o2) < 0.03, (l1, o1, l2_, o2)
+    for n in om.param_names():
+        assert np.all(np.isfinite(gm.get_parameter(n)))
+    st = gm.last_fit_stats()
+    assert st["partitions"] == 64 and st["steps"] == 4096 and st["kernel_launches"] == 1
