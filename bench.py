@@ -1,0 +1,251 @@
+#!/usr/bin/env python
+"""bench.py -- user-sequence training steps/s of the fit() hot path on B200 (BASELINE.json metric).
+
+A "step" of this benchmark is one pass (one epoch of fit) over a synthetic ML-100K-shaped interaction stream
+(configs[1] of BASELINE.json: 1,683 items, dim 32, every user-sequence 32 items => 31 timesteps, LSTM Normal,
+WARP, Adagrad lr 0.16 l2 4e-4).  `value` counts reference optimizer steps (= sub-sequences, sequence_model.rs:111)
+per second with the stream already resident in HBM; `e2e` is the same metric through the public C ABI from HOST
+buffers (CSR -> sbr_compressed_from_csr -> sbr_model_fit: H2D of the id stream and the schedule inside the timed
+region).  `--impl reference` times the CPU restatement of the reference path (oracle/, all host threads).
+
+Contract: python bench.py --gpus N --steps K --warmup W ; N > 1 under torchrun (one rank per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+NUM_ITEMS, SEQ_LEN, DIM = 1683, 32, 32
+LR, L2 = 0.16, 4e-4
+A_TRAIN_BYTES_PER_TIMESTEP = 60 * DIM + 52  # gather 12D+20 + Adagrad visit 48D+32  (= 1972 B at D=32)
+METRIC = "user-seq steps/sec"
+
+
+def make_stream(num_seqs, seed):
+    """2^k synthetic users x exactly 32 items, uniform over [1, N) (SURVEY 8d 'C2-stream', headline variant)."""
+    rng = np.random.default_rng(seed)
+    ptr = np.arange(num_seqs + 1, dtype=np.uint64) * np.uint64(SEQ_LEN)
+    ids = rng.integers(1, NUM_ITEMS, size=num_seqs * SEQ_LEN, dtype=np.uint64)
+    return ptr, ids
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, n in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(num_seqs, steps, warmup, threads, seed=1234):
+    """The reference arm / cpu_baseline: the oracle's fit() (sequence_model.rs:70-178 restated in C) with all host
+    threads, lock-free Hogwild (Parallelism::Asynchronous, the fastest reference mode), on a bounded sample of the
+    same workload.  Timed like the reference's tests time fit() (lstm.rs:436-438)."""
+    import oracle_lib as O
+    ptr, ids = make_stream(num_seqs, seed)
+    m = O.OracleModel("lstm", NUM_ITEMS, SEQ_LEN, embedding_dim=DIM, learning_rate=LR, l2_penalty=L2,
+                      lstm_variant="normal", loss="warp", optimizer="adagrad", parallelism="asynchronous",
+                      num_threads=threads, num_epochs=1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        rc, _ = m.fit(ptr, ids)
+        assert rc == 0
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return num_seqs * len(times) / sum(times), sum(times) / len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seqs", type=int, default=1 << 20, help="sub-sequences per GPU per step")
+    ap.add_argument("--cpu-seqs", type=int, default=0, help="sample size of the CPU arm (0 = auto)")
+    ap.add_argument("--threads", type=int, default=0, help="Hogwild partitions per GPU (0 = fill the device)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    config = {"workload": "ML-100K-shaped stream: LSTMVariant::Normal dim=32 seq=32 WARP Adagrad lr=0.16 l2=4e-4 "
+                          "(BASELINE configs[1])", "num_items": NUM_ITEMS, "seq_len": SEQ_LEN, "dim": DIM,
+              "item_distribution": "uniform[1,N)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n = args.cpu_seqs or 2048 * cores
+        value, sec = cpu_reference_run(n, args.steps, args.warmup, cores)
+        config.update({"seqs_per_step": n, "parallelism": "%d host threads, Hogwild" % cores})
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
+                             "sample": "%d sequences x %d items per step, oracle fit(), %d threads Hogwild" % (n, SEQ_LEN, cores)},
+            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    if pkg.device_count() < 1:
+        raise SystemExit("bench.py needs a B200: libsbr_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    pkg.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    S = args.seqs
+    ptr, ids = make_stream(S, 1000 + rank)  # every rank trains on its own shard of the stream (weak scaling)
+    seed = bytes((7 * rank + i) % 256 for i in range(16))
+    model = (pkg.lstm.Hyperparameters(NUM_ITEMS, SEQ_LEN).embedding_dim(DIM).learning_rate(LR).l2_penalty(L2)
+             .lstm_variant(pkg.LSTMVariant.Normal).loss(pkg.Loss.WARP).optimizer(pkg.Optimizer.Adagrad)
+             .parallelism(pkg.Parallelism.Asynchronous).num_epochs(1).num_threads(args.threads).from_seed(seed).build())
+
+    # ---------------- device-resident arm: `value` ----------------
+    data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=NUM_ITEMS).upload()
+    plan = model.fit_plan(data)
+    for _ in range(args.warmup):
+        plan.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    kernel_ms, launches, timesteps = 0.0, 0, 0
+    for _ in range(args.steps):
+        plan.run()  # blocks until the epoch's kernel has finished (loss read back)
+        st = plan.stats()
+        kernel_ms += st["train_kernel_ms"]; launches += st["kernel_launches"]; timesteps += st["timesteps"]
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    partitions = plan.stats()["partitions"]
+    steps_done = plan.stats()["steps"]  # per run
+    value = world * steps_done * args.steps / wall
+    kernel_ms_max = max_over_ranks(kernel_ms)
+    del plan
+
+    # ---------------- end-to-end arm through the C ABI from host buffers: `e2e` ----------------
+    h2d = d2h = 0
+    for _ in range(2):
+        model.fit(pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=NUM_ITEMS))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=NUM_ITEMS)  # host CSR in, nothing resident
+        model.fit(c)
+        st = model.last_fit_stats()
+        h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
+        del c
+    barrier()
+    e2e_wall = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * steps_done * args.steps / e2e_wall
+
+    if rank == 0:
+        peak, peak_kind = peaks()
+        per_launch_bytes = A_TRAIN_BYTES_PER_TIMESTEP * (timesteps / max(launches, 1))
+        per_launch_ms = kernel_ms / max(launches, 1)
+        achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(config, seqs_per_gpu_per_step=S, partitions_per_gpu=int(partitions),
+                           parallelism="hogwild partitions; one model replica per GPU" if world > 1 else "hogwild partitions",
+                           l2_policy="id stream (%d MiB/GPU) larger than L2; 215 KB item table is L2-resident by construction"
+                                     % (S * SEQ_LEN * 4 >> 20)),
+            "timesteps_per_s": value * (SEQ_LEN - 1),
+            "device_ms_per_step": kernel_ms_max / args.steps,
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_kind": peak_kind, "kernel": "lstm_train_kernel<32,8>",
+                         "algorithmic_bytes_per_timestep": A_TRAIN_BYTES_PER_TIMESTEP},
+        }
+        if not args.no_cpu_baseline:
+            n = args.cpu_seqs or 1024 * cores
+            cv, csec = cpu_reference_run(n, 2, 1, cores)
+            out["cpu_baseline"] = {"value": cv, "unit": "steps/s", "cores": cores, "kind": "port",
+                                   "sample": "%d sequences x %d items, oracle fit() 1 epoch x2 (+1 warm-up), %d threads Hogwild"
+                                             % (n, SEQ_LEN, cores)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -314,8 +314,8 @@ static void apply_update(sbo_model* m, sbo_ws* w) {
     const size_t D = m->D; const float lr = m->h.learning_rate, l2 = m->h.l2_penalty;
     const int adam = m->h.optimizer == SBO_OPT_ADAM;
     float c1 = 1, c2 = 1;
+    uint64_t t = ++m->num_updates; /* per-parameter num_updates, one per step() [wyrm-recalled] */
     if (adam) {
-        uint64_t t = ++m->num_updates; /* per-parameter num_updates, one per step() [wyrm-recalled] */
         c1 = 1.0f - powf(0.9f, (float)t); c2 = 1.0f - powf(0.999f, (float)t);
     }
     /* sparse rows: one update per recorded (row, grad) entry, in order, duplicates NOT merged */

@@ -101,12 +101,16 @@ def test_warm_restart_and_second_fit(pkg, oracle):
 
 @pytest.mark.parametrize("kind", ["ewma", "lstm"])
 def test_ml100k_shaped_epoch_single_thread(pkg, oracle, kind, ml100k):
-    """One epoch over real ML-100K sequences (first 150 users), seq 32 / dim 32 / WARP / Adagrad: config C1/C2."""
+    """One epoch over real ML-100K sequences (first 150 users), seq 32 / dim 32 / WARP / Adagrad: config C1/C2.
+    Element-wise parity needs a well-conditioned trajectory: at the recipe's lr = 0.16 the first Adagrad visit of an
+    element moves it by lr * sign(g) whatever |g| is, which turns 1-ulp differences in near-zero gradients into
+    0.32 jumps (measured: lr 0.01 -> max diff 5e-8, lr 0.16 -> O(1) after ~100 steps, on CPU-vs-CPU reorderings
+    too).  So: element-wise at lr 0.02 here, statistical (loss / MRR) at lr 0.16 in test_gpu_mrr.py."""
     nu = 150
     ptr = ml100k["user_ptr"][: nu + 1].astype(np.uint64)
     ids = ml100k["item_ids"][: int(ptr[-1])].astype(np.uint64)
     N = int(ml100k["num_items"])
-    gm, om = make_pair(pkg, oracle, kind, N, 32, 32, loss="warp", optimizer="adagrad", variant="normal", lr=0.16,
+    gm, om = make_pair(pkg, oracle, kind, N, 32, 32, loss="warp", optimizer="adagrad", variant="normal", lr=0.02,
                        l2=4e-4, epochs=1, threads=1)
     data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
     gl = gm.fit(data)
@@ -182,8 +186,6 @@ def test_hogwild_many_partitions_statistics(pkg, oracle, kind):
     data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
     l1 = gm.fit(data) / 64  # sum over partitions of per-partition means (sequence_model.rs:173-175)
     l2_ = gm.fit(data) / 64
-    om.h.num_threads = 1
-    import ctypes as C
     om1 = oracle.OracleModel(kind, N, T, embedding_dim=D, learning_rate=0.05, l2_penalty=0.0, lstm_variant="normal",
                              loss="bpr", optimizer="adagrad", num_epochs=1, num_threads=1, seed=bytes(range(1, 17)))
     for name in om1.param_names():
