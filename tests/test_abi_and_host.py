@@ -1,0 +1,130 @@
+"""CPU-side tests of the product library: it loads, exports every symbol include/sbr_b200.h declares, its host
+logic (CSR build, chunker) matches the oracle / the reference's golden vectors, and every compute entry point fails
+LOUDLY without a GPU (there is no CPU fallback).  No compute calls are made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "sbr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sbr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.lib()
+    syms = header_symbols()
+    assert len(syms) >= 45
+    for s in syms:
+        assert hasattr(lib, s), "libsbr_b200.so does not export %s" % s
+    assert sorted(pkg.EXPORTS) == syms  # the Python mirror binds exactly the declared surface
+
+
+def test_no_torch_in_abi_signatures():
+    src = open(os.path.join(ROOT, "include", "sbr_b200.h")).read()
+    assert "torch" not in src.lower() and "at::" not in src and "#include <cuda" not in src
+
+
+def test_chunk_golden_vector_through_abi(pkg):
+    """data.rs:630-662 through the product's chunker."""
+    inter = pkg.Interactions.from_interactions([pkg.Interaction(0, i, i) for i in range(5)])
+    assert inter.shape() == (1, 5)  # max + 1 (data.rs:202-203)
+    c = inter.to_compressed()
+    up, items, ts = c.arrays()
+    got = [items[s:s + n].tolist() for s, n in c.user_chunks(0, 3)]
+    assert got == [[0, 1], [2, 3, 4]]
+    assert [ts[s:s + n].tolist() for s, n in c.user_chunks(0, 3)] == [[0, 1], [2, 3, 4]]
+    with pytest.raises(pkg.SbrError):
+        c.user_chunks(1, 3)  # get_user(user_id >= num_users) is None (data.rs:278-280)
+
+
+def test_compress_matches_oracle_and_is_stable(pkg):
+    rng = np.random.default_rng(0)
+    for nu, ni, nnz in ((1, 1, 0), (5, 7, 1), (20, 20, 100), (300, 50, 5000)):
+        users = rng.integers(0, nu, size=nnz).astype(np.uint64)
+        items = rng.integers(0, ni, size=nnz).astype(np.uint64)
+        ts = rng.integers(0, 10, size=nnz).astype(np.uint64)  # few distinct timestamps => many ties
+        c = pkg.Interactions.from_arrays(users, items, ts, nu, ni).to_compressed()
+        up, ii, tt = c.arrays()
+        oup, oii, ott = O.compress(users, items, ts, nu)
+        assert np.array_equal(up, oup) and np.array_equal(ii, oii) and np.array_equal(tt, ott)
+        assert c.num_users() == nu and c.num_items() == ni and len(c) == nnz
+        # round trip (data.rs:588-627): to_interactions() gives back the same multiset
+        back = c.to_interactions()
+        a = sorted(zip(users.tolist(), items.tolist(), ts.tolist()))
+        b = sorted(zip(np.asarray(back._u).tolist(), np.asarray(back._i).tolist(), np.asarray(back._t).tolist()))
+        assert a == b
+
+
+def test_ml100k_through_product_csr(pkg, ml100k):
+    c = pkg.Interactions.from_arrays(ml100k["raw_users"], ml100k["raw_items"], ml100k["raw_ts"]).to_compressed()
+    assert c.shape() == (944, 1683)
+    up, ii, tt = c.arrays()
+    assert np.array_equal(up, ml100k["user_ptr"]) and np.array_equal(ii, ml100k["item_ids"])
+    assert np.array_equal(tt, ml100k["timestamps"])
+    # chunker agrees with the oracle on every user, at the three sequence lengths the configs use
+    for T in (32, 128, 200):
+        for u in range(0, 944, 37):
+            assert c.user_chunks(u, T) == O.chunks(int(up[u + 1] - up[u]), T)
+
+
+def test_invalid_arguments_are_status_codes(pkg):
+    with pytest.raises(pkg.SbrError):  # user id >= num_users: Rust would panic on the index
+        pkg.Interactions.from_arrays([5], [1], [0], num_users=3, num_items=4).to_compressed()
+    with pytest.raises(pkg.SbrError):
+        pkg.Interactions.from_arrays([1], [9], [0], num_users=3, num_items=4).to_compressed()
+    with pytest.raises(pkg.SbrError):
+        pkg.CompressedInteractions.from_csr([1, 2], [0, 0], None, num_items=3)  # ptr[0] != 0
+    with pytest.raises(pkg.SbrError):
+        pkg.CompressedInteractions.from_csr([0, 3, 2], [0, 0, 0], None, num_items=3)  # decreasing
+    h = pkg.ewma.Hyperparameters(10, 5)
+    with pytest.raises(pkg.SbrError):
+        h.loss(7)
+    with pytest.raises(pkg.SbrError):
+        h._set("sbr_hyper_lstm_variant", 0)  # EWMA has no variant (ewma.rs:45-57)
+
+
+def test_hyperparameter_builder_chains(pkg):
+    """lstm.rs:54-138: every setter returns the builder."""
+    h = (pkg.lstm.Hyperparameters(100, 32).learning_rate(0.16).l2_penalty(4e-4).embedding_dim(32).num_epochs(10)
+         .loss(pkg.Loss.WARP).lstm_variant(pkg.LSTMVariant.Normal).num_threads(2)
+         .parallelism(pkg.Parallelism.Synchronous).from_seed(bytes([42] * 16)).optimizer(pkg.Optimizer.Adagrad))
+    assert isinstance(h, pkg.lstm.Hyperparameters)
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="this check is for GPU-less boxes")
+def test_compute_fails_loudly_without_gpu(pkg):
+    assert pkg.device_count() == 0
+    with pytest.raises(pkg.SbrError) as e:
+        pkg.lstm.Hyperparameters(10, 4).build()
+    assert e.value.status == pkg.SBR_ERR_CUDA and "no CPU fallback" in str(e.value)
+    c = pkg.Interactions.from_arrays([0, 0, 0], [1, 2, 3], [0, 1, 2]).to_compressed()
+    with pytest.raises(pkg.SbrError) as e:
+        c.upload()
+    assert e.value.status == pkg.SBR_ERR_CUDA
+
+
+def test_product_never_touches_the_oracle():
+    """The product path must not route through oracle/: no source under the package or include/ mentions it."""
+    for base in ("sbr-rs_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            if "build" in dirpath:
+                continue
+            for f in files:
+                if f.endswith((".cu", ".cuh", ".h", ".cc", ".py", "Makefile")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    code = re.sub(r"//.*|/\*.*?\*/|#.*", "", txt)  # comments may cite the oracle, code may not
+                    assert "liboracle" not in code and "oracle_lib" not in code and "sbr_oracle.h" not in code, (dirpath, f)
+                    assert not re.search(r"\bsbo_\w+\s*\(", code), (dirpath, f)
+    # and the shared object has no undefined sbo_* symbols
+    import subprocess
+    out = subprocess.run(["nm", "-D", os.path.join(ROOT, "sbr-rs_b200", "libsbr_b200.so")], capture_output=True, text=True)
+    assert "sbo_" not in out.stdout
