@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -595,6 +596,7 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
     cudaStream_t st = m->stream;
     const size_t P = pl->P;
     pl->dev.epochs = (int)m->h.num_epochs;
+    { const char* f = getenv("SBR_DBG_FLAGS"); pl->dev.dbg_flags = f ? atoi(f) : 0; }
     pl->dev.adam_t0 = m->num_updates;
     CU(cudaMemsetAsync(pl->dev.loss_acc, 0, P * sizeof(float), st));
     CU(cudaMemsetAsync(pl->dev.examples, 0, P * sizeof(unsigned long long), st));

@@ -40,6 +40,7 @@ struct PlanDev {
     float* scratch;             // warp-private activations for backward
     size_t scratch_stride;      // floats per warp
     int epochs;
+    int dbg_flags;              // debugging switches (0 in production)
     unsigned long long adam_t0; // model num_updates before this run
 };
 
@@ -48,6 +49,8 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
 size_t train_scratch_floats_per_warp(const ModelDev& m);
 int train_auto_partitions(const ModelDev& m, int num_sms);
 bool train_supported(const ModelDev& m, const char** why);
+int lstm_kernel_choice(const ModelDev& m, uint32_t P);
+cudaError_t launch_lstm_tc(const ModelDev& m, const PlanDev& p, int nt, cudaStream_t st);
 
 cudaError_t launch_gather_rows(const ModelDev& m, const uint32_t* ids_dev, size_t n, float* out_dev, cudaStream_t st);
 cudaError_t launch_user_representations(const ModelDev& m, const uint64_t* ptr_dev, const uint32_t* ids_dev, size_t num_users,

@@ -6,6 +6,9 @@
 // lock-free in HBM/L2 exactly like Arc<HogwildParameter> (lstm.rs:175-181,259-260).  One launch runs all epochs.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "engine.h"
 
 namespace sbr {
@@ -455,9 +458,19 @@ size_t train_scratch_floats_per_warp(const ModelDev& m) {
 }
 
 int train_auto_partitions(const ModelDev& m, int num_sms) {
-    // resident warps per SM the kernels reach (registers / shared memory), see DESIGN.md
+    // EWMA / FFMA LSTM: resident warps per SM (registers / shared memory); tensor-core LSTM: 2 tiles of 128 per SM
+    if (m.model == MODEL_LSTM && m.D == 32) return num_sms * 256;
     int per_sm = m.model == MODEL_EWMA ? (m.D <= 64 ? 32 : 16) : 16;
     return num_sms * per_sm;
+}
+
+// which LSTM kernel a plan runs on: 0 = FFMA (exact fp32, warp per partition), 1/2 = tensor-core tiles per CTA
+int lstm_kernel_choice(const ModelDev& m, uint32_t P) {
+    const char* force = getenv("SBR_LSTM_KERNEL");
+    if (force && !strcmp(force, "ffma")) return 0;
+    if (m.model != MODEL_LSTM || m.D != 32 || P < 128 || P % 128 != 0) return 0;
+    if (force && !strcmp(force, "tc1")) return 1;
+    return P % 256 == 0 ? 2 : 1;
 }
 
 int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t st, cudaError_t* err) {
@@ -473,6 +486,9 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
             case 256: ewma_train_kernel<256><<<grid, block, 0, st>>>(m, p); break;
             default: *err = cudaErrorInvalidValue; return 0;
         }
+    } else if (int nt = lstm_kernel_choice(m, p.P)) {
+        *err = launch_lstm_tc(m, p, nt, st);
+        return 1;
     } else {
         dim3 block(kLstmWPC * 32), grid((p.P + kLstmWPC - 1) / kLstmWPC);
         if (m.D == 32) {

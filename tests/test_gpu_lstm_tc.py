@@ -1,0 +1,119 @@
+"""Tensor-core LSTM kernel (tcgen05 tiles, kernels_lstm_tc.cu) against the CPU oracle.
+
+The tile kernel is the throughput path (num_threads a multiple of 128): tf32 forward products, bf16 backward products,
+fp32 accumulation, MUFU exp/rcp/rsqrt.  Stated tolerance of this mode: one round of 128*NT sequences from identical
+parameters reproduces the oracle's parameters to |diff| <= 4e-4 at lr 0.05 (updates themselves are O(1e-2)), i.e.
+gradients to ~1 % -- the bf16 operand rounding.  Many partitions race (Hogwild), so the element-wise check uses a
+construction where the races cannot matter: every partition trains exactly one sequence over its own items, all
+gradients are taken at the initial parameters (the kernel computes a whole round before any dependent read), rows
+touched by two different sequences (colliding negatives) are excluded, and the dense step is one optimizer step on the
+round-summed gradient, which is this kernel's documented dense semantics.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import make_pair, stream_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def _adagrad(w, G, g, lr, l2):
+    g = np.float32(g) + w * np.float32(l2)
+    G = G + g * g
+    w = w - np.float32(lr) * g / np.sqrt(np.maximum(G, np.float32(1e-20)))
+    return w.astype(np.float32), G.astype(np.float32)
+
+
+@pytest.mark.parametrize("P,variant", [(128, "normal"), (256, "normal"), (256, "coupled")])
+def test_one_round_matches_oracle_gradients(pkg, oracle, P, variant):
+    N, T, D, lr, l2 = 60000, 8, 32, 0.05, 1e-3
+    ptr = (np.arange(P + 1) * T).astype(np.uint64)
+    ids = (1000 + np.arange(P * T)).astype(np.uint64)          # user u owns items 1000+8u .. 1000+8u+7
+    gm, om = make_pair(pkg, oracle, "lstm", N, T, D, loss="bpr", optimizer="adagrad", variant=variant, lr=lr, l2=l2,
+                       epochs=1, threads=P, scale=0.3)
+    rs = np.random.default_rng(9)
+    gm.set_parameter("lstm_weights", (rs.uniform(-0.3, 0.3, 2 * D * 4 * D)).astype(np.float32))
+    gm.set_parameter("lstm_biases", (rs.uniform(-0.3, 0.3, 4 * D)).astype(np.float32))
+    for n in ("item_embeddings", "item_biases", "lstm_weights", "lstm_biases"):
+        gm.set_parameter(n + ".s1", np.ones(len(gm.get_parameter(n)), dtype=np.float32))  # Adagrad G = 1: updates ~ lr * g
+    for n in om.param_names():
+        om.param(n)[:] = gm.get_parameter(n)
+        om.param(n + ".s1")[:] = 1.0
+    E0, b0 = om.param("item_embeddings").reshape(N, D).copy(), om.param("item_biases").copy()
+    W0 = np.concatenate([om.param("lstm_weights"), om.param("lstm_biases")]).copy()
+
+    # the schedule of sequence_model.rs:84-98 replayed with the oracle's rng primitives
+    L = oracle.lib()
+    rng = oracle.Rng(*gm.rng_state)
+    order = np.arange(P, dtype=np.uint32)
+    L.sbo_shuffle_u32(C.byref(rng), order.ctypes.data_as(oracle.u32p), P)
+    keys = []
+    for _ in range(P):
+        seed = bytes(L.sbo_rng_next_u32(C.byref(rng)) & 0xFF for _ in range(16))
+        keys.append(int.from_bytes(seed[:8], "little"))
+
+    data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
+    gm.fit(data)
+    assert gm.last_fit_stats()["partitions"] == P
+
+    E, GE = E0.copy(), np.ones_like(E0)
+    b, Gb = b0.copy(), np.ones_like(b0)
+    dense_sum = np.zeros_like(W0)
+    touched = {}
+    for p in range(P):
+        sq = int(order[p])
+        seq = ids[sq * T:(sq + 1) * T]
+        _, negs, dg = om.step(seq, key=keys[p], step=0, apply=False)
+        dense_sum += dg
+        rows, grads, brows, bgrads = om.last_sparse_grads()
+        for rrow in set(rows.tolist()) | set(brows.tolist()):
+            touched.setdefault(rrow, set()).add(p)
+        for rrow, gr in zip(rows.tolist(), grads):
+            E[rrow], GE[rrow] = _adagrad(E[rrow], GE[rrow], gr, lr, l2)
+        for rrow, gr in zip(brows.tolist(), bgrads.tolist()):
+            wv, gv = _adagrad(b[rrow:rrow + 1], Gb[rrow:rrow + 1], gr, lr, l2)
+            b[rrow], Gb[rrow] = wv[0], gv[0]
+    W1, _ = _adagrad(W0, np.ones_like(W0), dense_sum, lr, l2)
+
+    clean = np.array(sorted(k for k, v in touched.items() if len(v) == 1), dtype=np.int64)
+    assert len(clean) > 0.9 * len(touched)
+    gE = gm.get_parameter("item_embeddings").reshape(N, D)
+    gb = gm.get_parameter("item_biases")
+    gW = np.concatenate([gm.get_parameter("lstm_weights"), gm.get_parameter("lstm_biases")])
+    assert np.abs(E[clean] - E0[clean]).mean() > 5e-4            # the comparison is not vacuous
+    assert np.abs(gE[clean] - E[clean]).max() <= 4e-4, np.abs(gE[clean] - E[clean]).max()
+    assert np.abs(gb[clean] - b[clean]).max() <= 4e-4
+    dW = np.abs(W1 - W0)
+    err = np.abs(gW - W1)
+    assert dW.mean() > 1e-3
+    assert err.max() <= 1e-3 and err.mean() <= 1e-4, (err.max(), err.mean(), dW.mean())
+    untouched = np.setdiff1d(np.arange(N), np.array(sorted(touched), dtype=np.int64))
+    assert np.array_equal(gE[untouched], E0[untouched])          # rows nobody named are bit-identical
+
+
+@pytest.mark.parametrize("loss", ["bpr", "warp"])
+def test_tile_kernel_learns_like_the_exact_path(pkg, oracle, loss):
+    """Statistical parity on an ML-100K-shaped stream: per-epoch losses of the tile kernel (256 partitions) track the
+    exact FFMA kernel run with the same partition count, and parameters stay finite."""
+    import os
+    rng = np.random.default_rng(5)
+    N, T, D = 1683, 32, 32
+    ptr, ids = stream_csr(rng, 16384, N, 32)
+    losses = {}
+    for kern in ("ffma", "tc"):
+        if kern == "ffma":
+            os.environ["SBR_LSTM_KERNEL"] = "ffma"
+        else:
+            os.environ.pop("SBR_LSTM_KERNEL", None)
+        gm, _ = make_pair(pkg, oracle, "lstm", N, T, D, loss=loss, optimizer="adagrad", variant="normal", lr=0.05,
+                          l2=1e-4, epochs=1, threads=256)
+        data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
+        losses[kern] = [gm.fit(data) / 256 for _ in range(6)]
+        for n in ("item_embeddings", "item_biases", "lstm_weights", "lstm_biases"):
+            assert np.all(np.isfinite(gm.get_parameter(n))), (kern, n)
+    os.environ.pop("SBR_LSTM_KERNEL", None)
+    a, b = np.array(losses["ffma"]), np.array(losses["tc"])
+    assert b[-1] < b[0]
+    assert np.max(np.abs(a - b)) < 0.02, (a, b)
