@@ -527,7 +527,7 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     size_t P = m->h.num_threads;
     if (P == 0) {
         const size_t autoP = (size_t)train_auto_partitions(m->dev, device_info().sms);
-        P = std::min(autoP, std::max<size_t>(1, nsub / 32));
+        P = std::min(autoP, std::max<size_t>(1, nsub / 16));
     }
     if (P > nsub) return fail(SBR_ERR_INVALID_ARGUMENT, "num_threads exceeds the number of sub-sequences (the reference panics in chunks_mut(0))");
     const size_t n = nsub / P;  // :91, remainder dropped by the zip at :94-96

@@ -145,10 +145,19 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
     const size_t nd = m.ndense;
     const bool coupled = m.variant == 1;
     const int T = m.T;
-    // tile scratch, structure-of-arrays so that lane == sequence accesses are coalesced: [T][8][32 d][128 seq], then G, NEG [T][128]
+    // tile scratch, 16-byte structure-of-arrays so that lane == sequence accesses are coalesced (512 B per warp
+    // instruction): [T][8 arrays][8 chunks of 4 d][128 seq] float4, then G, NEG [T][128]
     float* sbase = pl.scratch + (size_t)tile_gid * 128 * pl.scratch_stride;
     float* G_ = sbase + (size_t)T * 8 * 32 * 128; uint32_t* NEG = reinterpret_cast<uint32_t*>(G_ + (size_t)T * 128);
-    auto sc = [&](int t, int which, int d) -> float* { return sbase + (((size_t)t * 8 + which) * 32 + d) * 128 + r; };
+    auto sc4 = [&](int t, int which, int c4) -> float4* {
+        return reinterpret_cast<float4*>(sbase) + (((size_t)t * 8 + which) * 8 + c4) * 128 + r;
+    };
+    // pull one timestep of the tile's scratch (128 KB = 1024 lines) towards L2: 8 lines per thread
+    auto prefetch_step = [&](int t) {
+        const char* base = reinterpret_cast<const char*>(sbase) + (size_t)t * 8 * 32 * 128 * 4 + (size_t)r * 8 * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i * 128));
+    };
 
     // ---- one-time setup ----
     if (tid < 32) tmem_alloc<(NT == 1 ? 256 : 512)>(tmem_ptr);
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                     }
                     if (act) {
 #pragma unroll
-                        for (int d = 0; d < 32; ++d) *sc(t, SX, d) = x[d];
+                        for (int c4 = 0; c4 < 8; ++c4) *sc4(t, SX, c4) = make_float4(x[4 * c4], x[4 * c4 + 1], x[4 * c4 + 2], x[4 * c4 + 3]);
                     }
                 }
                 fence_async_smem();
@@ -270,11 +279,20 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                         const float og = fast_sigmoid(po[j] + bias_s[96 + d]);
                         const float cn = f * c[d] + ig * gg;
                         const float hn = og * fast_tanh(cn);
-                        if (act) {
-                            c[d] = cn; h[d] = hn;
-                            *sc(t, SF, d) = f; *sc(t, SI, d) = ig; *sc(t, SG, d) = gg; *sc(t, SO, d) = og;
-                            *sc(t, SC, d) = cn; *sc(t, SH, d) = hn;
-                        } else h[d] = 0.0f;
+                        if (act) { c[d] = cn; h[d] = hn; } else h[d] = 0.0f;
+                        pf[j] = f; pi[j] = ig; pg[j] = gg; po[j] = og;
+                    }
+                    if (act) {
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const int c4 = db * 2 + hf, q = hf * 4;
+                            *sc4(t, SF, c4) = make_float4(pf[q], pf[q + 1], pf[q + 2], pf[q + 3]);
+                            *sc4(t, SI, c4) = make_float4(pi[q], pi[q + 1], pi[q + 2], pi[q + 3]);
+                            *sc4(t, SG, c4) = make_float4(pg[q], pg[q + 1], pg[q + 2], pg[q + 3]);
+                            *sc4(t, SO, c4) = make_float4(po[q], po[q + 1], po[q + 2], po[q + 3]);
+                            *sc4(t, SC, c4) = make_float4(c[4 * c4], c[4 * c4 + 1], c[4 * c4 + 2], c[4 * c4 + 3]);
+                            *sc4(t, SH, c4) = make_float4(h[4 * c4], h[4 * c4 + 1], h[4 * c4 + 2], h[4 * c4 + 3]);
+                        }
                     }
                 }
                 tc_fence_before_sync();  // TMEM reads ordered before the next MMA (issued after the next tile barrier)
@@ -307,7 +325,9 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                     else { const float v = 1.0f + ngs - pos; l = v > 0.0f ? v : 0.0f; g = v > 0.0f ? 1.0f : 0.0f; }
                     loss_seq += l;
 #pragma unroll
-                    for (int d = 0; d < 32; ++d) *sc(t, SDQ, d) = g * (qv[d] - pv[d]);
+                    for (int c4 = 0; c4 < 8; ++c4)
+                        *sc4(t, SDQ, c4) = make_float4(g * (qv[4 * c4] - pv[4 * c4]), g * (qv[4 * c4 + 1] - pv[4 * c4 + 1]),
+                                                       g * (qv[4 * c4 + 2] - pv[4 * c4 + 2]), g * (qv[4 * c4 + 3] - pv[4 * c4 + 3]));
                     G_[(size_t)t * 128 + r] = g; NEG[(size_t)t * 128 + r] = neg;
                 }
             }
@@ -322,35 +342,45 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
             for (int d = 0; d < 32; ++d) { dh_rec[d] = 0.0f; dc_rec[d] = 0.0f; }
             for (int t = Tmax - 1; t >= 0; --t) {
                 const bool act = t < Tn;
-                float ht[32];
                 float g = 0.0f; uint32_t neg = 0, in = 0, out = 0;
                 if (act) { g = G_[(size_t)t * 128 + r]; neg = NEG[(size_t)t * 128 + r]; in = __ldg(ids + t); out = __ldg(ids + t + 1); }
+                if (t >= 3) prefetch_step(t - 3);   // older timesteps have been evicted to HBM by the forward stream
 #pragma unroll
                 for (int db = 0; db < 4; ++db) {
                     float df[8], di[8], dg[8], dO[8], hp8[8], x8[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int d = db * 8 + j;
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int c4 = db * 2 + hf;
+                        float4 f4, i4, g4, o4, ct4, dq4, cp4, h4, hp4, x4;
+                        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (act) {
-                            const float f = *sc(t, SF, d), ig = *sc(t, SI, d), gg = *sc(t, SG, d), og = *sc(t, SO, d);
-                            const float ct = *sc(t, SC, d), dq = *sc(t, SDQ, d);
-                            const float cp = t > 0 ? *sc(t - 1, SC, d) : 0.0f;
-                            ht[d] = *sc(t, SH, d);
-                            hp8[j] = t > 0 ? *sc(t - 1, SH, d) : 0.0f;
-                            x8[j] = *sc(t, SX, d);
-                            const float tcv = fast_tanh(ct);
-                            const float dh = dh_rec[d] + dq;
+                            f4 = *sc4(t, SF, c4); i4 = *sc4(t, SI, c4); g4 = *sc4(t, SG, c4); o4 = *sc4(t, SO, c4);
+                            ct4 = *sc4(t, SC, c4); dq4 = *sc4(t, SDQ, c4); h4 = *sc4(t, SH, c4); x4 = *sc4(t, SX, c4);
+                            cp4 = t > 0 ? *sc4(t - 1, SC, c4) : z4; hp4 = t > 0 ? *sc4(t - 1, SH, c4) : z4;
+                        } else { f4 = i4 = g4 = o4 = ct4 = dq4 = cp4 = h4 = hp4 = x4 = z4; }
+                        // gradient of the two rows that only need h_t goes straight to the staging slice
+                        *reinterpret_cast<float4*>(stage_b + lane * kSS + c4 * 4) = make_float4(g * h4.x, g * h4.y, g * h4.z, g * h4.w);
+                        const float fa[4] = {f4.x, f4.y, f4.z, f4.w}, ia[4] = {i4.x, i4.y, i4.z, i4.w}, ga[4] = {g4.x, g4.y, g4.z, g4.w};
+                        const float oa[4] = {o4.x, o4.y, o4.z, o4.w}, ca[4] = {ct4.x, ct4.y, ct4.z, ct4.w}, qa[4] = {dq4.x, dq4.y, dq4.z, dq4.w};
+                        const float pa[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
+                        hp8[hf * 4] = hp4.x; hp8[hf * 4 + 1] = hp4.y; hp8[hf * 4 + 2] = hp4.z; hp8[hf * 4 + 3] = hp4.w;
+                        x8[hf * 4] = x4.x; x8[hf * 4 + 1] = x4.y; x8[hf * 4 + 2] = x4.z; x8[hf * 4 + 3] = x4.w;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int d = c4 * 4 + e, j = hf * 4 + e;
+                            const float tcv = fast_tanh(ca[e]);
+                            const float dh = dh_rec[d] + qa[e];
                             const float d_o = dh * tcv;
-                            const float dc = dc_rec[d] + dh * og * (1.0f - tcv * tcv);
-                            float d_f = dc * cp, d_i = dc * gg;
-                            const float d_g = dc * ig;
-                            dc_rec[d] = dc * f;
+                            const float dc = dc_rec[d] + dh * oa[e] * (1.0f - tcv * tcv);
+                            float d_f = dc * pa[e], d_i = dc * ga[e];
+                            const float d_g = dc * ia[e];
+                            dc_rec[d] = act ? dc * fa[e] : 0.0f;
                             if (coupled) { d_f -= d_i; d_i = 0.0f; }
-                            df[j] = d_f * f * (1.0f - f);
-                            di[j] = coupled ? 0.0f : d_i * ig * (1.0f - ig);
-                            dg[j] = d_g * (1.0f - gg * gg);
-                            dO[j] = d_o * og * (1.0f - og);
-                        } else { df[j] = di[j] = dg[j] = dO[j] = 0.0f; ht[d] = 0.0f; hp8[j] = 0.0f; x8[j] = 0.0f; }
+                            df[j] = d_f * fa[e] * (1.0f - fa[e]);
+                            di[j] = coupled ? 0.0f : d_i * ia[e] * (1.0f - ia[e]);
+                            dg[j] = d_g * (1.0f - ga[e] * ga[e]);
+                            dO[j] = d_o * oa[e] * (1.0f - oa[e]);
+                        }
                     }
                     *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 0 + db, 16)) = pack_bf16x8(df);
                     *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 4 + db, 16)) = pack_bf16x8(di);
@@ -374,7 +404,7 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                     mma_commit(mbar + tile);
                 }
                 // overlap with the MMAs: the two visits that need only h_t  (t descending: E[neg], E[out], ..)
-                stage_write_row(stage_b, lane, ht, g);
+                __syncwarp();
                 coop_update(m.E, RS, neg, act, lane, stage_b, 1.0f, o);
                 coop_update(m.E, RS, out, act, lane, stage_b, -1.0f, o);
                 mbar_wait(mbar + tile, phase); phase ^= 1;
