@@ -126,6 +126,21 @@ sbr_status sbr_model_get_rng_state(const sbr_model* m, uint32_t out[4]);
 sbr_status sbr_model_set_rng_state(sbr_model* m, const uint32_t state[4]);
 void sbr_model_free(sbr_model* m);
 
+/* ------------------------------------------------ multi-GPU (one process per GPU) ------------------------- */
+/* The reference shares ONE parameter set between its worker threads (Arc<HogwildParameter>, lstm.rs:175-181).  Across
+ * GPUs the same is done over NVLink: the item table, biases and their optimizer state are row-sharded (item_id %
+ * world) and every rank's training kernel gathers / updates remote rows directly in the owner's HBM through CUDA-IPC
+ * peer mappings (no staging copies, no collective on the data path); the small dense parameters live on rank 0.
+ * Protocol: every rank calls sbr_hyper_shard(rank, world) before build, exports sbr_model_ipc_handle_size() bytes
+ * with sbr_model_ipc_export, the host program all-gathers them in rank order (any transport), and every rank calls
+ * sbr_model_ipc_attach.  Ranks then call sbr_model_fit concurrently, each on its own users' interactions. */
+sbr_status sbr_hyper_shard(sbr_hyperparameters* h, int rank, int world);   /* world in {1,2,4,8} */
+/* Same sharded addressing with all shards in this process / on this device (used by single-GPU tests). */
+sbr_status sbr_hyper_virtual_shards(sbr_hyperparameters* h, int shards);
+size_t sbr_model_ipc_handle_size(void);
+sbr_status sbr_model_ipc_export(const sbr_model* m, void* out);
+sbr_status sbr_model_ipc_attach(sbr_model* m, const void* all_handles /* world * handle_size bytes, rank order */);
+
 /* ------------------------------------------- device-resident fit schedule --------------------------------- */
 typedef struct {
     uint64_t steps;          /* optimizer steps = sub-sequences processed (sequence_model.rs:111) */

@@ -42,6 +42,8 @@ EXPORTS = [
     "sbr_model_mrr_score", "sbr_model_gather_rows", "sbr_model_embedding_dim", "sbr_model_num_items",
     "sbr_model_parameter_len", "sbr_model_get_parameter", "sbr_model_set_parameter", "sbr_model_get_num_updates",
     "sbr_model_set_num_updates", "sbr_model_get_rng_state", "sbr_model_set_rng_state", "sbr_model_free",
+    "sbr_hyper_shard", "sbr_hyper_virtual_shards", "sbr_model_ipc_handle_size", "sbr_model_ipc_export",
+    "sbr_model_ipc_attach",
     "sbr_fit_plan_create", "sbr_fit_plan_run", "sbr_fit_plan_stats", "sbr_fit_plan_free", "sbr_model_last_fit_stats",
 ]
 
@@ -136,6 +138,11 @@ def lib():
     L.sbr_model_get_rng_state.argtypes = [vp, C.POINTER(C.c_uint32)]
     L.sbr_model_set_rng_state.argtypes = [vp, C.POINTER(C.c_uint32)]
     L.sbr_model_free.argtypes = [vp]
+    L.sbr_hyper_shard.argtypes = [vp, C.c_int, C.c_int]
+    L.sbr_hyper_virtual_shards.argtypes = [vp, C.c_int]
+    L.sbr_model_ipc_handle_size.restype = C.c_size_t
+    L.sbr_model_ipc_export.argtypes = [vp, C.c_void_p]
+    L.sbr_model_ipc_attach.argtypes = [vp, C.c_void_p]
     L.sbr_fit_plan_create.argtypes = [vp, vp, C.POINTER(vp)]
     L.sbr_fit_plan_run.argtypes = [vp, f32p]
     L.sbr_fit_plan_stats.argtypes = [vp, C.POINTER(FitStats)]
@@ -392,6 +399,15 @@ class _Hyperparameters:
     def optimizer(self, v):
         return self._set("sbr_hyper_optimizer", int(v))
 
+    def shard(self, rank, world):
+        """one process per GPU: this rank owns item rows with id % world == rank (sbr_hyper_shard)"""
+        _check(lib().sbr_hyper_shard(self._h, int(rank), int(world)))
+        return self
+
+    def virtual_shards(self, shards):
+        _check(lib().sbr_hyper_virtual_shards(self._h, int(shards)))
+        return self
+
     def from_seed(self, seed):
         s = (C.c_uint8 * 16)(*bytes(seed))
         _check(lib().sbr_hyper_from_seed(self._h, s))
@@ -483,6 +499,16 @@ class _Model:
     def rng_state(self, v):
         st = (C.c_uint32 * 4)(*v)
         _check(lib().sbr_model_set_rng_state(self._m, st))
+
+    def ipc_export(self):
+        buf = C.create_string_buffer(lib().sbr_model_ipc_handle_size())
+        _check(lib().sbr_model_ipc_export(self._m, buf))
+        return buf.raw
+
+    def ipc_attach(self, all_handles):
+        """all_handles: list of per-rank blobs from ipc_export(), in rank order"""
+        blob = b"".join(all_handles)
+        _check(lib().sbr_model_ipc_attach(self._m, C.create_string_buffer(blob, len(blob))))
 
     def last_fit_stats(self):
         s = FitStats()

@@ -139,6 +139,8 @@ struct sbr_hyperparameters {
     uint8_t seed[16];
     size_t num_threads = 0;                                              // lstm.rs:68 (0 = fill the device)
     size_t num_epochs = 10;                                              // lstm.rs:69
+    int shard_rank = 0, shard_world = 1;   // one process per GPU: this rank owns rows with id % world == rank
+    int virtual_shards = 1;                // > 1: shard the table inside this process (exercises the sharded addressing)
 };
 
 struct sbr_model {
@@ -149,10 +151,17 @@ struct sbr_model {
     cudaStream_t stream = nullptr;
     mutable std::mutex mu;
     sbr_fit_stats last{};
+    // sharding: own[i] != 0 => Es[i]/Bs[i] were cudaMalloc'ed here; otherwise they are CUDA-IPC mappings of a peer
+    bool own[8] = {false, false, false, false, false, false, false, false};
+    float* own_dense = nullptr;   // this process's dense buffer (dev.dense points at rank 0's after attach)
+    bool attached = true;         // false between build() and sbr_model_ipc_attach() when shard_world > 1
     ~sbr_model() {
-        if (dev.E) cudaFree(dev.E);
-        if (dev.B) cudaFree(dev.B);
-        if (dev.dense) cudaFree(dev.dense);
+        for (int i = 0; i < 8; ++i) {
+            if (own[i]) { if (dev.Es[i]) cudaFree(dev.Es[i]); if (dev.Bs[i]) cudaFree(dev.Bs[i]); }
+            else { if (dev.Es[i]) cudaIpcCloseMemHandle(dev.Es[i]); if (dev.Bs[i]) cudaIpcCloseMemHandle(dev.Bs[i]); }
+        }
+        if (dev.dense && dev.dense != own_dense) cudaIpcCloseMemHandle(dev.dense);
+        if (own_dense) cudaFree(own_dense);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -401,9 +410,21 @@ sbr_status sbr_hyper_build(sbr_hyperparameters* hp, sbr_model** out) {
     auto bail = [&](cudaError_t e, const char* what) { sbr_status r = cuda_fail(e, what); delete m; return r; };
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
-    if ((e = cudaMalloc(&d.E, (size_t)d.N * d.S * d.D * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc item table");
-    if ((e = cudaMalloc(&d.B, (size_t)d.N * sizeof(float4))) != cudaSuccess) return bail(e, "cudaMalloc bias table");
+    // item table + optimizer state, row-sharded by id % G (G = 1: one shard)
+    const int G = h.shard_world > 1 ? h.shard_world : h.virtual_shards;
+    d.gmask = (uint32_t)G - 1;
+    d.gshift = 0; while ((1 << d.gshift) < G) ++d.gshift;
+    d.own_shard = h.shard_world > 1 ? h.shard_rank : -1;
+    m->attached = h.shard_world <= 1;
+    for (int g = 0; g < G; ++g) {
+        if (h.shard_world > 1 && g != h.shard_rank) continue;   // peers' shards are mapped by sbr_model_ipc_attach
+        const size_t rows = ((size_t)d.N + G - 1 - g) / G;       // ids g, g+G, g+2G, ...
+        if ((e = cudaMalloc(&d.Es[g], std::max<size_t>(rows, 1) * d.S * d.D * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc item table");
+        if ((e = cudaMalloc(&d.Bs[g], std::max<size_t>(rows, 1) * sizeof(float4))) != cudaSuccess) return bail(e, "cudaMalloc bias table");
+        m->own[g] = true;
+    }
     if ((e = cudaMalloc(&d.dense, 3 * d.ndense * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc dense parameters");
+    m->own_dense = d.dense;
     // parameter init (lstm.rs:174-186): embeddings N(0, 1/D) in HBM, biases 0, alpha 0, LSTM U(+-1/sqrt(D)) [wyrm-recalled]
     const uint64_t seed64 = xs_next_u64(m->rng);
     if ((e = launch_init_embeddings(d, seed64, m->stream)) != cudaSuccess) return bail(e, "init embeddings");
@@ -418,6 +439,61 @@ sbr_status sbr_hyper_build(sbr_hyperparameters* hp, sbr_model** out) {
     if ((e = cudaMemcpyAsync(d.dense, dense.data(), dense.size() * sizeof(float), cudaMemcpyHostToDevice, m->stream)) != cudaSuccess) return bail(e, "upload dense");
     if ((e = cudaStreamSynchronize(m->stream)) != cudaSuccess) return bail(e, "build sync");
     *out = m;
+    return SBR_OK;
+}
+
+// --------------------------------------------------------------------------------------------- multi-GPU ----
+sbr_status sbr_hyper_shard(sbr_hyperparameters* h, int rank, int world) {
+    if (!h) return fail(SBR_ERR_INVALID_ARGUMENT, "null hyperparameters");
+    if (!(world == 1 || world == 2 || world == 4 || world == 8) || rank < 0 || rank >= world)
+        return fail(SBR_ERR_INVALID_ARGUMENT, "world must be 1, 2, 4 or 8 and 0 <= rank < world");
+    h->shard_rank = rank; h->shard_world = world; h->virtual_shards = 1;
+    return SBR_OK;
+}
+sbr_status sbr_hyper_virtual_shards(sbr_hyperparameters* h, int g) {
+    if (!h) return fail(SBR_ERR_INVALID_ARGUMENT, "null hyperparameters");
+    if (!(g == 1 || g == 2 || g == 4 || g == 8)) return fail(SBR_ERR_INVALID_ARGUMENT, "shard count must be 1, 2, 4 or 8");
+    h->virtual_shards = g; h->shard_rank = 0; h->shard_world = 1;
+    return SBR_OK;
+}
+
+size_t sbr_model_ipc_handle_size(void) { return 3 * sizeof(cudaIpcMemHandle_t); }
+
+sbr_status sbr_model_ipc_export(const sbr_model* m, void* out) {
+    if (!m || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    sbr_status s = require_device();
+    if (s) return s;
+    const int r = m->h.shard_rank;
+    if (m->h.shard_world <= 1) return fail(SBR_ERR_INVALID_ARGUMENT, "model was not built with sbr_hyper_shard");
+    cudaIpcMemHandle_t* hs = reinterpret_cast<cudaIpcMemHandle_t*>(out);
+    CU(cudaIpcGetMemHandle(&hs[0], m->dev.Es[r]));
+    CU(cudaIpcGetMemHandle(&hs[1], m->dev.Bs[r]));
+    CU(cudaIpcGetMemHandle(&hs[2], m->own_dense));
+    return SBR_OK;
+}
+
+sbr_status sbr_model_ipc_attach(sbr_model* m, const void* all_handles) {
+    if (!m || !all_handles) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    sbr_status s = require_device();
+    if (s) return s;
+    const int W = m->h.shard_world, r = m->h.shard_rank;
+    if (W <= 1) return fail(SBR_ERR_INVALID_ARGUMENT, "model was not built with sbr_hyper_shard");
+    if (m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "peers already attached");
+    std::lock_guard<std::mutex> lk(m->mu);
+    const cudaIpcMemHandle_t* hs = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);
+    for (int g = 0; g < W; ++g) {
+        if (g == r) continue;
+        void* pe = nullptr; void* pb = nullptr;
+        CU(cudaIpcOpenMemHandle(&pe, hs[3 * g + 0], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&pb, hs[3 * g + 1], cudaIpcMemLazyEnablePeerAccess));
+        m->dev.Es[g] = static_cast<float*>(pe); m->dev.Bs[g] = static_cast<float4*>(pb);
+    }
+    if (r != 0) {  // the dense parameters (LSTM weights / alpha) live on rank 0; everyone updates them Hogwild
+        void* pd = nullptr;
+        CU(cudaIpcOpenMemHandle(&pd, hs[2], cudaIpcMemLazyEnablePeerAccess));
+        m->dev.dense = static_cast<float*>(pd);
+    }
+    m->attached = true;
     return SBR_OK;
 }
 
@@ -440,6 +516,7 @@ static sbr_status param_io(sbr_model* m, const char* name, float* host, size_t l
     ParamRef r; s = resolve_param(m, name, &r);
     if (s) return s;
     if (len != r.len) return fail(SBR_ERR_INVALID_ARGUMENT, "parameter length mismatch");
+    if (!set && r.kind != 2 && !m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before reading the table");
     std::lock_guard<std::mutex> lk(m->mu);
     cudaStream_t st = m->stream;
     if (r.kind == 2) {
@@ -500,6 +577,7 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     sbr_status s = require_device();
     if (s) return s;
     if (c->num_items > m->dev.N) return fail(SBR_ERR_INVALID_ARGUMENT, "interactions.num_items exceeds the model's num_items");
+    if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before using it");
     const double t0 = now_ms();
     const size_t T = (size_t)m->dev.T;
     // sequence_model.rs:76-83: chunk every user, keep len > 2
@@ -655,6 +733,7 @@ sbr_status sbr_model_last_fit_stats(const sbr_model* m, sbr_fit_stats* out) {
 sbr_status sbr_model_user_representations(const sbr_model* m, const uint64_t* ptr, const uint64_t* item_ids, size_t num_users,
                                           float* out) {
     if (!m || !ptr || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before using it");
     sbr_status s = require_device();
     if (s) return s;
     if (num_users == 0) return SBR_OK;
@@ -689,6 +768,7 @@ sbr_status sbr_model_user_representation(const sbr_model* m, const uint64_t* ite
 
 sbr_status sbr_model_predict(const sbr_model* m, const float* user, const uint64_t* item_ids, size_t k, float* out) {
     if (!m || !user || (k && (!item_ids || !out))) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before using it");
     sbr_status s = require_device();
     if (s) return s;
     if (k == 0) return SBR_OK;
@@ -721,6 +801,7 @@ sbr_status sbr_model_predict(const sbr_model* m, const float* user, const uint64
 
 sbr_status sbr_model_mrr_score(const sbr_model* m, const sbr_compressed* test, float* out) {
     if (!m || !test || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before using it");
     sbr_status s = require_device();
     if (s) return s;
     if (test->num_items > m->dev.N) return fail(SBR_ERR_INVALID_ARGUMENT, "test.num_items exceeds the model's num_items");
@@ -753,6 +834,7 @@ sbr_status sbr_model_mrr_score(const sbr_model* m, const sbr_compressed* test, f
 
 sbr_status sbr_model_gather_rows(const sbr_model* m, const uint64_t* item_ids, size_t n, float* out) {
     if (!m || (n && (!item_ids || !out))) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before using it");
     sbr_status s = require_device();
     if (s) return s;
     if (n == 0) return SBR_OK;

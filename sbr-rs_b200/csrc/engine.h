@@ -16,8 +16,14 @@ struct ModelDev {
     uint32_t N;
     int D, T;
     int S;           // floats-vectors per item row record: 2 (w,G) Adagrad, 3 (w,m,v) Adam
-    float* E;        // [N][S][D]
-    float4* B;       // [N] {b, s1, s2, pad}
+    // Item table, row-sharded by item id: shard = id & gmask, local row = id >> gshift (G = gmask+1 is 1, 2, 4 or 8).
+    // With G == 1 everything is in Es[0] / Bs[0].  With G > 1 a shard is either local memory (virtual shards, tests)
+    // or a peer GPU's memory mapped through CUDA IPC (one process per GPU; loads/stores travel over NVLink).
+    float* Es[8];    // [rows of shard][S][D]
+    float4* Bs[8];   // [rows of shard] {b, s1, s2, pad}
+    uint32_t gmask;
+    int gshift;
+    int own_shard;   // >= 0: only this shard is written by init / set_parameter (multi-process); -1: all shards are ours
     float* dense;    // [3][ndense]  w | s1 | s2  (LSTM: W[2D][4][D] then bias[4][D]; EWMA: alpha[D])
     size_t ndense;
     float lr, l2;
@@ -43,6 +49,13 @@ struct PlanDev {
     int dbg_flags;              // debugging switches (0 in production)
     unsigned long long adam_t0; // model num_updates before this run
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float* item_rec(const ModelDev& m, uint32_t id) {
+    return m.Es[id & m.gmask] + (size_t)(id >> m.gshift) * ((size_t)m.S * m.D);
+}
+__device__ __forceinline__ float4* bias_rec(const ModelDev& m, uint32_t id) { return m.Bs[id & m.gmask] + (id >> m.gshift); }
+#endif
 
 // launchers (kernels_train.cu / kernels_infer.cu); all enqueue on `st` and return the launch count
 int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t st, cudaError_t* err);

@@ -14,15 +14,14 @@ namespace {
 
 // ---- K1: bit-exact row gather.  One thread moves one 16-byte piece of one row: a warp covers 512 contiguous
 // output bytes and 512/(4D) whole table rows; loads bypass L1 (random rows, no reuse), stores stream.
-__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ E, int D, size_t RS,
-                                                          const uint32_t* __restrict__ ids, size_t n,
+__global__ void __launch_bounds__(256) gather_rows_kernel(ModelDev m, const uint32_t* __restrict__ ids, size_t n,
                                                           float* __restrict__ out) {
-    const int q = D >> 2;  // float4 per row
+    const int q = m.D >> 2;  // float4 per row
     const size_t total = n * (size_t)q;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t r = i / q; const int c = (int)(i - r * q);
         const uint32_t id = __ldg(ids + r);
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(E + (size_t)id * RS) + c);
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(item_rec(m, id)) + c);
         __stcs(reinterpret_cast<float4*>(out) + i, v);
     }
 }
@@ -38,7 +37,7 @@ __device__ __forceinline__ void ewma_represent(const ModelDev& m, const uint32_t
     for (int v = 0; v < V; ++v) { a[v] = sigmoidf_(al[v]); s[v] = 0.0f; }
     for (int t = 0; t < n; ++t) {
         const uint32_t in = ids ? __ldg(ids + t) : 0u;
-        row_load_cg<D>(m.E + (size_t)in * RS, lane, x);
+        row_load_cg<D>(item_rec(m, in), lane, x);
 #pragma unroll
         for (int v = 0; v < V; ++v) s[v] = t == 0 ? x[v] : a[v] * s[v] + (1.0f - a[v]) * x[v];
     }
@@ -57,7 +56,7 @@ __device__ __forceinline__ void lstm_represent(const ModelDev& m, const uint32_t
     for (int t = 0; t < n; ++t) {
         const uint32_t in = ids ? __ldg(ids + t) : 0u;
         float x[1];
-        row_load_cg<D>(m.E + (size_t)in * RS, lane, x);
+        row_load_cg<D>(item_rec(m, in), lane, x);
         float pre[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) pre[q] = __ldcg(B + q * D + ld);
@@ -99,7 +98,7 @@ __global__ void __launch_bounds__(128) user_rep_kernel(ModelDev m, const uint64_
 // predict_single: bias + dot(user, row).  One thread per item, 16-byte loads.
 template <int D>
 __device__ __forceinline__ float score_item(const ModelDev& m, const float* __restrict__ user, uint32_t id) {
-    const float4* row = reinterpret_cast<const float4*>(m.E + (size_t)id * m.S * D);
+    const float4* row = reinterpret_cast<const float4*>(item_rec(m, id));
     float acc = 0.0f;
 #pragma unroll
     for (int c = 0; c < D / 4; ++c) {
@@ -107,7 +106,7 @@ __device__ __forceinline__ float score_item(const ModelDev& m, const float* __re
         acc = fmaf(user[4 * c], r.x, acc); acc = fmaf(user[4 * c + 1], r.y, acc);
         acc = fmaf(user[4 * c + 2], r.z, acc); acc = fmaf(user[4 * c + 3], r.w, acc);
     }
-    return __ldcg(reinterpret_cast<const float*>(m.B + id)) + acc;
+    return __ldcg(reinterpret_cast<const float*>(bias_rec(m, id))) + acc;
 }
 
 template <int D>
@@ -172,25 +171,27 @@ __global__ void __launch_bounds__(256) init_embeddings_kernel(ModelDev m, uint64
         const float u2 = ((float)(uint32_t)(v & 0xffffffu) + 0.5f) * (1.0f / 16777216.0f);
         const float z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
         const size_t r = i / m.D; const int d = (int)(i - r * m.D);
-        float* rec = m.E + r * (size_t)m.S * m.D;
+        if (m.own_shard >= 0 && (int)(r & m.gmask) != m.own_shard) continue;
+        float* rec = item_rec(m, (uint32_t)r);
         rec[d] = z * sd;
         for (int s = 1; s < m.S; ++s) rec[s * m.D + d] = 0.0f;
     }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += (size_t)gridDim.x * blockDim.x)
-        m.B[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m.own_shard < 0 || (int)(i & m.gmask) == m.own_shard) *bias_rec(m, (uint32_t)i) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 __global__ void __launch_bounds__(256) pack_rows_kernel(ModelDev m, int slot, const float* __restrict__ packed, float* out, int dir) {
     const size_t total = (size_t)m.N * m.D;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t r = i / m.D; const int d = (int)(i - r * m.D);
-        float* cell = m.E + (r * m.S + slot) * (size_t)m.D + d;
+        if (dir == 0 && m.own_shard >= 0 && (int)(r & m.gmask) != m.own_shard) continue;
+        float* cell = item_rec(m, (uint32_t)r) + (size_t)slot * m.D + d;
         if (dir == 0) *cell = packed[i]; else out[i] = *cell;
     }
 }
 __global__ void __launch_bounds__(256) pack_bias_kernel(ModelDev m, int slot, const float* __restrict__ packed, float* out, int dir) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += (size_t)gridDim.x * blockDim.x) {
-        float* cell = reinterpret_cast<float*>(m.B + i) + slot;
+        float* cell = reinterpret_cast<float*>(bias_rec(m, i)) + slot;
         if (dir == 0) *cell = packed[i]; else out[i] = *cell;
     }
 }
@@ -217,7 +218,7 @@ inline int grid_for(size_t n, int block, int cap = 148 * 16) {
 cudaError_t launch_gather_rows(const ModelDev& m, const uint32_t* ids, size_t n, float* out, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const size_t total = n * (size_t)(m.D / 4);
-    gather_rows_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(m.E, m.D, (size_t)m.S * m.D, ids, n, out);
+    gather_rows_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(m, ids, n, out);
     return cudaGetLastError();
 }
 

@@ -61,12 +61,12 @@ __device__ __forceinline__ void fast_adam(float& w, float& m, float& v, float g,
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kSS = 36;
 
-__device__ __forceinline__ void coop_gather(const float* __restrict__ E, size_t RS, uint32_t my_id, int lane, float* stage) {
+__device__ __forceinline__ void coop_gather(const ModelDev& m, uint32_t my_id, int lane, float* stage) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int row = 4 * i + (lane >> 3);
         const uint32_t id = __shfl_sync(kFull, my_id, row);
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(E + (size_t)id * RS) + (lane & 7));
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(item_rec(m, id)) + (lane & 7));
         *reinterpret_cast<float4*>(stage + row * kSS + (lane & 7) * 4) = v;
     }
     __syncwarp();
@@ -85,37 +85,59 @@ __device__ __forceinline__ void stage_write_row(float* stage, int lane, const fl
             make_float4(scale * v[4 * c], scale * v[4 * c + 1], scale * v[4 * c + 2], scale * v[4 * c + 3]);
     __syncwarp();
 }
-// sparse optimizer visit of the 32 rows named by the lanes' ids with the staged gradients (times `sign`)
-__device__ __forceinline__ void coop_update(float* __restrict__ E, size_t RS, uint32_t my_id, bool my_act, int lane,
+// sparse optimizer visit of the 32 rows named by the lanes' ids with the staged gradients (times `sign`).
+// All 16 row loads are issued before the first use: the 8 row groups belong to 8 x 4 different sequences, and two
+// sequences naming the same row is the same benign Hogwild race as between warps (last store wins).
+__device__ __forceinline__ void coop_update(const ModelDev& m, uint32_t my_id, bool my_act, int lane,
                                             const float* stage, float sign, const OptCfg& o) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int row = 4 * i + (lane >> 3);
-        const uint32_t id = __shfl_sync(kFull, my_id, row);
-        const bool a = __shfl_sync(kFull, (int)my_act, row) != 0;
-        if (a) {
-            const float4 g = *reinterpret_cast<const float4*>(stage + row * kSS + (lane & 7) * 4);
-            float* rec = E + (size_t)id * RS + (lane & 7) * 4;
-            float4 w = __ldcg(reinterpret_cast<const float4*>(rec)), s = __ldcg(reinterpret_cast<const float4*>(rec + kD));
-            if (!o.adam) {
-                fast_adagrad(w.x, s.x, sign * g.x, o.lr, o.l2); fast_adagrad(w.y, s.y, sign * g.y, o.lr, o.l2);
-                fast_adagrad(w.z, s.z, sign * g.z, o.lr, o.l2); fast_adagrad(w.w, s.w, sign * g.w, o.lr, o.l2);
-            } else {
-                float4 v = __ldcg(reinterpret_cast<const float4*>(rec + 2 * kD));
-                fast_adam(w.x, s.x, v.x, sign * g.x, o); fast_adam(w.y, s.y, v.y, sign * g.y, o);
-                fast_adam(w.z, s.z, v.z, sign * g.z, o); fast_adam(w.w, s.w, v.w, sign * g.w, o);
-                __stcg(reinterpret_cast<float4*>(rec + 2 * kD), v);
+    for (int hb = 0; hb < 2; ++hb) {   // two batches of four row groups: 8 loads in flight, 32 registers
+        float* rec[4]; bool a[4]; float4 w[4], s[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = 4 * (hb * 4 + i) + (lane >> 3);
+            const uint32_t id = __shfl_sync(kFull, my_id, row);
+            a[i] = __shfl_sync(kFull, (int)my_act, row) != 0;
+            rec[i] = item_rec(m, id) + (lane & 7) * 4;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (a[i]) { w[i] = __ldcg(reinterpret_cast<const float4*>(rec[i])); s[i] = __ldcg(reinterpret_cast<const float4*>(rec[i] + kD)); }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (a[i]) {
+                const int row = 4 * (hb * 4 + i) + (lane >> 3);
+                const float4 g = *reinterpret_cast<const float4*>(stage + row * kSS + (lane & 7) * 4);
+                if (!o.adam) {
+                    fast_adagrad(w[i].x, s[i].x, sign * g.x, o.lr, o.l2); fast_adagrad(w[i].y, s[i].y, sign * g.y, o.lr, o.l2);
+                    fast_adagrad(w[i].z, s[i].z, sign * g.z, o.lr, o.l2); fast_adagrad(w[i].w, s[i].w, sign * g.w, o.lr, o.l2);
+                } else {
+                    float4 v = __ldcg(reinterpret_cast<const float4*>(rec[i] + 2 * kD));
+                    fast_adam(w[i].x, s[i].x, v.x, sign * g.x, o); fast_adam(w[i].y, s[i].y, v.y, sign * g.y, o);
+                    fast_adam(w[i].z, s[i].z, v.z, sign * g.z, o); fast_adam(w[i].w, s[i].w, v.w, sign * g.w, o);
+                    __stcg(reinterpret_cast<float4*>(rec[i] + 2 * kD), v);
+                }
+                __stcg(reinterpret_cast<float4*>(rec[i]), w[i]); __stcg(reinterpret_cast<float4*>(rec[i] + kD), s[i]);
             }
-            __stcg(reinterpret_cast<float4*>(rec), w); __stcg(reinterpret_cast<float4*>(rec + kD), s);
         }
     }
     __syncwarp();
 }
-__device__ __forceinline__ void thread_update_bias(float4* rec, float g, const OptCfg& o) {
-    float4 r = __ldcg(rec);
-    if (!o.adam) fast_adagrad(r.x, r.y, g, o.lr, o.l2);
-    else fast_adam(r.x, r.y, r.z, g, o);
-    __stcg(rec, r);
+// the two bias visits of one timestep (b[neg] += g-step, b[out] -= g-step); loads first unless they alias
+__device__ __forceinline__ void thread_update_biases(const ModelDev& m, uint32_t neg, uint32_t out, float g, const OptCfg& o) {
+    float4* rn = bias_rec(m, neg); float4* ro = bias_rec(m, out);
+    float4 a = __ldcg(rn);
+    if (neg != out) {
+        float4 b = __ldcg(ro);
+        if (!o.adam) { fast_adagrad(a.x, a.y, g, o.lr, o.l2); fast_adagrad(b.x, b.y, -g, o.lr, o.l2); }
+        else { fast_adam(a.x, a.y, a.z, g, o); fast_adam(b.x, b.y, b.z, -g, o); }
+        __stcg(rn, a); __stcg(ro, b);
+    } else {
+        if (!o.adam) { fast_adagrad(a.x, a.y, g, o.lr, o.l2); fast_adagrad(a.x, a.y, -g, o.lr, o.l2); }
+        else { fast_adam(a.x, a.y, a.z, g, o); fast_adam(a.x, a.y, a.z, -g, o); }
+        __stcg(rn, a);
+    }
 }
 __device__ __forceinline__ void tile_bar(int tile) { asm volatile("bar.sync %0, 128;" ::"r"(tile + 1) : "memory"); }
 
@@ -141,7 +163,6 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
     const uint32_t tile_gid = blockIdx.x * NT + tile;
     const uint32_t p = tile_gid * 128u + r;
     const bool live = p < pl.P;
-    const size_t RS = (size_t)m.S * kD;
     const size_t nd = m.ndense;
     const bool coupled = m.variant == 1;
     const int T = m.T;
@@ -233,7 +254,7 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                 if (act) { in = __ldg(ids + t); out = __ldg(ids + t + 1); }
                 {
                     float x[32];
-                    coop_gather(m.E, RS, in, lane, stage_f);       // item_embeddings.index(input), one line per row
+                    coop_gather(m, in, lane, stage_f);       // item_embeddings.index(input), one line per row
                     stage_read_row(stage_f, lane, x);
                     __syncwarp();
 #pragma unroll
@@ -260,10 +281,10 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                 }
                 // overlap with the MMA: target rows
                 float pv[32], qv[32];
-                coop_gather(m.E, RS, out, lane, stage_f);
+                coop_gather(m, out, lane, stage_f);
                 stage_read_row(stage_f, lane, pv);
                 __syncwarp();
-                const float bp = act ? __ldcg(reinterpret_cast<const float*>(m.B + out)) : 0.0f;
+                const float bp = act ? __ldcg(reinterpret_cast<const float*>(bias_rec(m, out))) : 0.0f;
                 mbar_wait(mbar + tile, phase); phase ^= 1;
                 tc_fence_after_sync();
 #pragma unroll
@@ -307,14 +328,14 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                 for (int j = 0; j < tries; ++j) {
                     if (__all_sync(kFull, done)) break;
                     const uint32_t cand = done ? neg : draw_item(key, step, (uint32_t)t, (uint32_t)j, pl.neg_range);
-                    coop_gather(m.E, RS, cand, lane, stage_f);
+                    coop_gather(m, cand, lane, stage_f);
                     if (!done) {
                         neg = cand;
                         stage_read_row(stage_f, lane, qv);
                         ngs = 0.0f;
 #pragma unroll
                         for (int d = 0; d < 32; ++d) ngs = fmaf(h[d], qv[d], ngs);
-                        ngs += __ldcg(reinterpret_cast<const float*>(m.B + neg));
+                        ngs += __ldcg(reinterpret_cast<const float*>(bias_rec(m, neg)));
                         if (1.0f - pos + ngs > 0.0f) done = true;
                     }
                     __syncwarp();
@@ -344,7 +365,7 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                 const bool act = t < Tn;
                 float g = 0.0f; uint32_t neg = 0, in = 0, out = 0;
                 if (act) { g = G_[(size_t)t * 128 + r]; neg = NEG[(size_t)t * 128 + r]; in = __ldg(ids + t); out = __ldg(ids + t + 1); }
-                if (t >= 3) prefetch_step(t - 3);   // older timesteps have been evicted to HBM by the forward stream
+                if (t >= 2) prefetch_step(t - 2);   // older timesteps have been evicted to HBM by the forward stream
 #pragma unroll
                 for (int db = 0; db < 4; ++db) {
                     float df[8], di[8], dg[8], dO[8], hp8[8], x8[8];
@@ -405,8 +426,8 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                 }
                 // overlap with the MMAs: the two visits that need only h_t  (t descending: E[neg], E[out], ..)
                 __syncwarp();
-                coop_update(m.E, RS, neg, act, lane, stage_b, 1.0f, o);
-                coop_update(m.E, RS, out, act, lane, stage_b, -1.0f, o);
+                coop_update(m, neg, act, lane, stage_b, 1.0f, o);
+                coop_update(m, out, act, lane, stage_b, -1.0f, o);
                 mbar_wait(mbar + tile, phase); phase ^= 1;
                 tc_fence_after_sync();
                 float dx[32];
@@ -420,11 +441,8 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                 }
                 tc_fence_before_sync();
                 stage_write_row(stage_b, lane, dx, 1.0f);
-                coop_update(m.E, RS, in, act, lane, stage_b, 1.0f, o);   // .. E[in], b[neg], b[out]
-                if (act) {
-                    thread_update_bias(m.B + neg, g, o);
-                    thread_update_bias(m.B + out, -g, o);
-                }
+                coop_update(m, in, act, lane, stage_b, 1.0f, o);   // .. E[in], b[neg], b[out]
+                if (act) thread_update_biases(m, neg, out, g, o);
             }
             if (live) { loss_acc += loss_seq; ex += (unsigned long long)Tn; }
 

@@ -47,13 +47,13 @@ __device__ __forceinline__ void score_and_sample(const ModelDev& m, int lane, co
                                                  uint64_t key, uint64_t step, uint32_t t, uint32_t range, float (&p)[VecOf<D>::V],
                                                  float (&q)[VecOf<D>::V], uint32_t& neg, float& pos, float& ngs) {
     const size_t RS = (size_t)m.S * D;
-    row_load_cg<D>(m.E + (size_t)out * RS, lane, p);
-    pos = warp_dot<D>(h, p) + __ldcg(reinterpret_cast<const float*>(m.B + out));
+    row_load_cg<D>(item_rec(m, out), lane, p);
+    pos = warp_dot<D>(h, p) + __ldcg(reinterpret_cast<const float*>(bias_rec(m, out)));
     const int tries = m.loss == 2 ? 5 : 1;
     for (int j = 0; j < tries; ++j) {
         neg = draw_item(key, step, t, (uint32_t)j, range);
-        row_load_cg<D>(m.E + (size_t)neg * RS, lane, q);
-        ngs = warp_dot<D>(h, q) + __ldcg(reinterpret_cast<const float*>(m.B + neg));
+        row_load_cg<D>(item_rec(m, neg), lane, q);
+        ngs = warp_dot<D>(h, q) + __ldcg(reinterpret_cast<const float*>(bias_rec(m, neg)));
         if (1.0f - pos + ngs > 0.0f) break;  // warp-uniform
     }
 }
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl)
             for (int t = 0; t < Tn; ++t) {
                 const uint32_t in = __ldg(ids + t), out = __ldg(ids + t + 1);
                 float x[V], pv[V], qv[V];
-                row_load_cg<D>(m.E + (size_t)in * RS, lane, x);  // item_embeddings.index(input)
+                row_load_cg<D>(item_rec(m, in), lane, x);  // item_embeddings.index(input)
 #pragma unroll
                 for (int v = 0; v < V; ++v) s[v] = t == 0 ? x[v] : a[v] * s[v] + (1.0f - a[v]) * x[v];
                 vec_store<D>(S_ + (size_t)t * D, lane, s);
@@ -163,12 +163,12 @@ __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl)
                 }
 #pragma unroll
                 for (int v = 0; v < V; ++v) { gn[v] = g * st[v]; gp[v] = -g * st[v]; }
-                update_row<D>(m.E + (size_t)neg * RS, lane, gn, o);
-                update_row<D>(m.E + (size_t)out * RS, lane, gp, o);
-                update_row<D>(m.E + (size_t)in * RS, lane, dx, o);
+                update_row<D>(item_rec(m, neg), lane, gn, o);
+                update_row<D>(item_rec(m, out), lane, gp, o);
+                update_row<D>(item_rec(m, in), lane, dx, o);
                 if (lane == 0) {
-                    update_bias(m.B + neg, g, o);
-                    update_bias(m.B + out, -g, o);
+                    update_bias(bias_rec(m, neg), g, o);
+                    update_bias(bias_rec(m, out), -g, o);
                 }
                 __syncwarp();
             }
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(WPC * 32) lstm_train_kernel(ModelDev m, PlanDe
                 for (int t = 0; t < Tn; ++t) {
                     const uint32_t in = __ldg(ids + t), out = __ldg(ids + t + 1);
                     float x[1], hv[1], pv[1], qv[1];
-                    row_load_cg<D>(m.E + (size_t)in * RS, lane, x);
+                    row_load_cg<D>(item_rec(m, in), lane, x);
                     if (act) { myz[lane] = h; myz[D + lane] = x[0]; }
                     __syncwarp();
                     float4 pre = Bs[ld];
@@ -356,12 +356,12 @@ __global__ void __launch_bounds__(WPC * 32) lstm_train_kernel(ModelDev m, PlanDe
                     if constexpr (D == 32) { dh_rec = part[0]; dx = part[1]; }
                     else { dx = __shfl_sync(kFull, part[0], (lane + 16) & 31); dh_rec = act ? part[0] : 0.0f; }
                     float gn[1] = {g * ht}, gp[1] = {-g * ht}, gx[1] = {dx};
-                    update_row<D>(m.E + (size_t)neg * RS, lane, gn, o);
-                    update_row<D>(m.E + (size_t)out * RS, lane, gp, o);
-                    update_row<D>(m.E + (size_t)in * RS, lane, gx, o);
+                    update_row<D>(item_rec(m, neg), lane, gn, o);
+                    update_row<D>(item_rec(m, out), lane, gp, o);
+                    update_row<D>(item_rec(m, in), lane, gx, o);
                     if (lane == 0) {
-                        update_bias(m.B + neg, g, o);
-                        update_bias(m.B + out, -g, o);
+                        update_bias(bias_rec(m, neg), g, o);
+                        update_bias(bias_rec(m, out), -g, o);
                     }
                     __syncwarp();
                 }
