@@ -169,10 +169,20 @@ def main():
 
     S = args.seqs
     ptr, ids = make_stream(S, 1000 + rank)  # every rank trains on its own shard of the stream (weak scaling)
-    seed = bytes((7 * rank + i) % 256 for i in range(16))
-    model = (pkg.lstm.Hyperparameters(NUM_ITEMS, SEQ_LEN).embedding_dim(DIM).learning_rate(LR).l2_penalty(L2)
+    # N > 1: ONE model shared by all ranks -- the item table is row-sharded (id % N) and every rank's kernel reads /
+    # updates remote rows in the owner's HBM over NVLink (CUDA-IPC peer mappings); no collective on the data path.
+    seed = bytes(range(16))  # same init on every rank
+    hyper = (pkg.lstm.Hyperparameters(NUM_ITEMS, SEQ_LEN).embedding_dim(DIM).learning_rate(LR).l2_penalty(L2)
              .lstm_variant(pkg.LSTMVariant.Normal).loss(pkg.Loss.WARP).optimizer(pkg.Optimizer.Adagrad)
-             .parallelism(pkg.Parallelism.Asynchronous).num_epochs(1).num_threads(args.threads).from_seed(seed).build())
+             .parallelism(pkg.Parallelism.Asynchronous).num_epochs(1).num_threads(args.threads).from_seed(seed))
+    if world > 1:
+        model = hyper.shard(rank, world).build()
+        blobs = [None] * world
+        dist.all_gather_object(blobs, model.ipc_export())
+        model.ipc_attach(blobs)
+        dist.barrier()
+    else:
+        model = hyper.build()
 
     # ---------------- device-resident arm: `value` ----------------
     data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=NUM_ITEMS).upload()
@@ -223,7 +233,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(config, seqs_per_gpu_per_step=S, partitions_per_gpu=int(partitions),
-                           parallelism="hogwild partitions; one model replica per GPU" if world > 1 else "hogwild partitions",
+                           parallelism=("hogwild partitions; one shared model, item table row-sharded over %d GPUs via NVLink peer access" % world)
+                           if world > 1 else "hogwild partitions",
                            l2_policy="id stream (%d MiB/GPU) larger than L2; 215 KB item table is L2-resident by construction"
                                      % (S * SEQ_LEN * 4 >> 20)),
             "timesteps_per_s": value * (SEQ_LEN - 1),
