@@ -210,11 +210,11 @@ def main():
     # ---------------- end-to-end arm through the C ABI from host buffers: `e2e` ----------------
     h2d = d2h = 0
     for _ in range(2):
-        model.fit(pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=NUM_ITEMS))
+        model.fit(pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=NUM_ITEMS, borrow=True))
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        c = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=NUM_ITEMS)  # host CSR in, nothing resident
+        c = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=NUM_ITEMS, borrow=True)  # host CSR in, nothing resident
         model.fit(c)
         st = model.last_fit_stats()
         h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]

@@ -62,6 +62,10 @@ sbr_status sbr_compressed_from_triplets(const uint64_t* user_ids, const uint64_t
 /* Adopt an existing CSR (the three Vec fields at data.rs:231-233). timestamps may be NULL. Copies. */
 sbr_status sbr_compressed_from_csr(const uint64_t* user_pointers, const uint64_t* item_ids, const uint64_t* timestamps,
                                    size_t num_users, size_t num_items, sbr_compressed** out);
+/* Zero-copy variant: the handle only borrows the three arrays (they must outlive it), like the `&CompressedInteractions`
+ * that fit() takes in the reference (lstm.rs:395). */
+sbr_status sbr_compressed_borrow_csr(const uint64_t* user_pointers, const uint64_t* item_ids, const uint64_t* timestamps,
+                                     size_t num_users, size_t num_items, sbr_compressed** out);
 size_t sbr_compressed_num_users(const sbr_compressed* c); /* data.rs:293-295 */
 size_t sbr_compressed_num_items(const sbr_compressed* c); /* data.rs:298-300 */
 size_t sbr_compressed_len(const sbr_compressed* c);

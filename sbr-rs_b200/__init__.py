@@ -31,7 +31,7 @@ SBR_ERR_CUDA, SBR_ERR_NCCL, SBR_ERR_UNSUPPORTED = 4, 5, 6
 # every symbol include/sbr_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "sbr_last_error_string", "sbr_device_count", "sbr_set_device",
-    "sbr_compressed_from_triplets", "sbr_compressed_from_csr", "sbr_compressed_num_users", "sbr_compressed_num_items",
+    "sbr_compressed_from_triplets", "sbr_compressed_from_csr", "sbr_compressed_borrow_csr", "sbr_compressed_num_users", "sbr_compressed_num_items",
     "sbr_compressed_len", "sbr_compressed_borrow", "sbr_compressed_user_chunks", "sbr_compressed_upload",
     "sbr_compressed_free",
     "sbr_lstm_hyperparameters_new", "sbr_ewma_hyperparameters_new", "sbr_hyper_learning_rate", "sbr_hyper_l2_penalty",
@@ -97,6 +97,7 @@ def lib():
     L.sbr_last_error_string.restype = C.c_char_p
     L.sbr_compressed_from_triplets.argtypes = [u64p, u64p, u64p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(vp)]
     L.sbr_compressed_from_csr.argtypes = [u64p, u64p, u64p, C.c_size_t, C.c_size_t, C.POINTER(vp)]
+    L.sbr_compressed_borrow_csr.argtypes = [u64p, u64p, u64p, C.c_size_t, C.c_size_t, C.POINTER(vp)]
     for f in ("num_users", "num_items", "len"):
         getattr(L, "sbr_compressed_" + f).restype = C.c_size_t
         getattr(L, "sbr_compressed_" + f).argtypes = [vp]
@@ -277,15 +278,19 @@ class CompressedInteractions:
         return cls(h)
 
     @classmethod
-    def from_csr(cls, user_pointers, item_ids, timestamps=None, num_items=None):
+    def from_csr(cls, user_pointers, item_ids, timestamps=None, num_items=None, borrow=False):
+        """borrow=True: zero-copy view of the caller's arrays (sbr_compressed_borrow_csr); they are kept alive here."""
         up, ii = _u64(user_pointers), _u64(item_ids)
         tt = _u64(timestamps) if timestamps is not None else None
         if num_items is None:
             num_items = int(ii.max()) + 1 if len(ii) else 0
         h = C.c_void_p()
-        _check(lib().sbr_compressed_from_csr(_p(up, u64p), _p(ii, u64p), _p(tt, u64p) if tt is not None else None,
-                                             len(up) - 1, num_items, C.byref(h)))
-        return cls(h)
+        fn = lib().sbr_compressed_borrow_csr if borrow else lib().sbr_compressed_from_csr
+        _check(fn(_p(up, u64p), _p(ii, u64p), _p(tt, u64p) if tt is not None else None, len(up) - 1, num_items, C.byref(h)))
+        self = cls(h)
+        if borrow:
+            self._keep = (up, ii, tt)
+        return self
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:

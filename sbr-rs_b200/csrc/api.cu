@@ -9,11 +9,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <mutex>
 #include <new>
 #include <string>
@@ -99,9 +102,21 @@ sbr_status upload_ids_u32(const uint64_t* src, size_t n, uint32_t* dst, cudaStre
         const size_t cnt = std::min(Staging::kElems, n - done);
         if (used[b]) CU(cudaEventSynchronize(g_staging.ev[b]));
         uint32_t* out = g_staging.buf[b];
-        uint64_t bad = 0;
-        for (size_t i = 0; i < cnt; ++i) { const uint64_t v = src[done + i]; bad |= (uint64_t)(v >= bound); out[i] = (uint32_t)v; }
-        if (bad) return fail(SBR_ERR_INVALID_ARGUMENT, "item id out of range");
+        std::atomic<uint64_t> bad{0};
+        auto narrow = [&](size_t lo, size_t hi) {
+            uint64_t bd = 0;
+            for (size_t i = lo; i < hi; ++i) { const uint64_t v = src[done + i]; bd |= (uint64_t)(v >= bound); out[i] = (uint32_t)v; }
+            if (bd) bad.store(1);
+        };
+        const size_t nth = cnt >= (1u << 20) ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        if (nth <= 1) narrow(0, cnt);
+        else {
+            std::vector<std::thread> th;
+            const size_t per = (cnt + nth - 1) / nth;
+            for (size_t k = 0; k < nth; ++k) th.emplace_back(narrow, std::min(cnt, k * per), std::min(cnt, (k + 1) * per));
+            for (auto& t : th) t.join();
+        }
+        if (bad.load()) return fail(SBR_ERR_INVALID_ARGUMENT, "item id out of range");
         CU(cudaMemcpyAsync(dst + done, out, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         CU(cudaEventRecord(g_staging.ev[b], st));
         used[b] = true; b ^= 1; done += cnt;
@@ -118,7 +133,10 @@ sbr_status upload_ids_u32(const uint64_t* src, size_t n, uint32_t* dst, cudaStre
 // ============================================================================================================
 struct sbr_compressed {
     size_t num_users = 0, num_items = 0;
-    std::vector<uint64_t> user_ptr, item_ids, timestamps;
+    std::vector<uint64_t> user_ptr, item_ids, timestamps;   // owned storage (empty when borrowed)
+    const uint64_t* up_ = nullptr; const uint64_t* ii_ = nullptr; const uint64_t* tt_ = nullptr;  // views actually used
+    size_t nnz_ = 0;
+    void own_views() { up_ = user_ptr.data(); ii_ = item_ids.data(); tt_ = timestamps.data(); nnz_ = item_ids.size(); }
     // lazily created HBM mirror (immutable data => safe to share between const users)
     mutable std::mutex mu;
     mutable uint32_t* d_item_ids = nullptr;
@@ -155,6 +173,7 @@ struct sbr_model {
     bool own[8] = {false, false, false, false, false, false, false, false};
     float* own_dense = nullptr;   // this process's dense buffer (dev.dense points at rank 0's after attach)
     bool attached = true;         // false between build() and sbr_model_ipc_attach() when shard_world > 1
+    float* scratch_cache = nullptr; size_t scratch_cap = 0; bool scratch_busy = false;  // grow-only activation scratch
     ~sbr_model() {
         for (int i = 0; i < 8; ++i) {
             if (own[i]) { if (dev.Es[i]) cudaFree(dev.Es[i]); if (dev.Bs[i]) cudaFree(dev.Bs[i]); }
@@ -162,6 +181,7 @@ struct sbr_model {
         }
         if (dev.dense && dev.dense != own_dense) cudaIpcCloseMemHandle(dev.dense);
         if (own_dense) cudaFree(own_dense);
+        if (scratch_cache) cudaFree(scratch_cache);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -174,6 +194,7 @@ struct sbr_fit_plan {
     uint64_t steps_per_run = 0, timesteps_per_epoch = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     sbr_fit_stats stats{};
+    bool scratch_borrowed = false;
     ~sbr_fit_plan() {
         if (d_seq_start) cudaFree(d_seq_start);
         if (d_seq_len) cudaFree(d_seq_len);
@@ -183,7 +204,8 @@ struct sbr_fit_plan {
         if (dev.step_ctr) cudaFree(dev.step_ctr);
         if (dev.loss_acc) cudaFree(dev.loss_acc);
         if (dev.examples) cudaFree(dev.examples);
-        if (dev.scratch) cudaFree(dev.scratch);
+        if (dev.scratch && !scratch_borrowed) cudaFree(dev.scratch);
+        if (scratch_borrowed && model) model->scratch_busy = false;
         for (cudaEvent_t e : {ev0, ev1, evk0, evk1}) if (e) cudaEventDestroy(e);
     }
 };
@@ -193,19 +215,19 @@ namespace {
 sbr_status ensure_uploaded(const sbr_compressed* c, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(c->mu);
     c->upload_bytes = 0;
-    if (c->d_item_ids || c->item_ids.empty()) return SBR_OK;
+    if (c->d_item_ids || c->nnz_ == 0) return SBR_OK;
     sbr_status s = require_device();
     if (s) return s;
     uint32_t* d = nullptr; uint64_t* dp = nullptr;
-    CU(cudaMalloc(&d, std::max<size_t>(c->item_ids.size(), 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&d, std::max<size_t>(c->nnz_, 1) * sizeof(uint32_t)));
     size_t bytes = 0;
-    s = upload_ids_u32(c->item_ids.data(), c->item_ids.size(), d, st, c->num_items, &bytes);
+    s = upload_ids_u32(c->ii_, c->nnz_, d, st, c->num_items, &bytes);
     if (s) { cudaFree(d); return s; }
-    if (cudaMalloc(&dp, c->user_ptr.size() * sizeof(uint64_t)) != cudaSuccess) { cudaFree(d); return cuda_fail(cudaGetLastError(), "cudaMalloc user_ptr"); }
-    cudaError_t e = cudaMemcpyAsync(dp, c->user_ptr.data(), c->user_ptr.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+    if (cudaMalloc(&dp, (c->num_users + 1) * sizeof(uint64_t)) != cudaSuccess) { cudaFree(d); return cuda_fail(cudaGetLastError(), "cudaMalloc user_ptr"); }
+    cudaError_t e = cudaMemcpyAsync(dp, c->up_, (c->num_users + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { cudaFree(d); cudaFree(dp); return cuda_fail(e, "upload user_ptr"); }
-    bytes += c->user_ptr.size() * sizeof(uint64_t);
+    bytes += (c->num_users + 1) * sizeof(uint64_t);
     c->d_item_ids = d; c->d_user_ptr = dp; c->upload_bytes = bytes;
     return SBR_OK;
 }
@@ -281,6 +303,7 @@ sbr_status sbr_compressed_from_triplets(const uint64_t* user_ids, const uint64_t
         c->user_ptr[user_ids[s] + 1] += 1;
     }
     for (size_t u = 1; u <= num_users; ++u) c->user_ptr[u] += c->user_ptr[u - 1];  // data.rs:253-255
+    c->own_views();
     *out = c;
     return SBR_OK;
 }
@@ -301,20 +324,37 @@ sbr_status sbr_compressed_from_csr(const uint64_t* user_pointers, const uint64_t
     c->item_ids.assign(item_ids, item_ids + nnz);   // range-checked when narrowed for upload
     if (timestamps) c->timestamps.assign(timestamps, timestamps + nnz);
     else c->timestamps.assign(nnz, 0);
+    c->own_views();
+    *out = c;
+    return SBR_OK;
+}
+
+sbr_status sbr_compressed_borrow_csr(const uint64_t* user_pointers, const uint64_t* item_ids, const uint64_t* timestamps,
+                                     size_t num_users, size_t num_items, sbr_compressed** out) {
+    if (!out || !user_pointers) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if (num_items > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "num_items must fit in 32 bits");
+    if (user_pointers[0] != 0) return fail(SBR_ERR_INVALID_ARGUMENT, "user_pointers[0] must be 0");
+    for (size_t u = 0; u < num_users; ++u)
+        if (user_pointers[u + 1] < user_pointers[u]) return fail(SBR_ERR_INVALID_ARGUMENT, "user_pointers must be non-decreasing");
+    if (user_pointers[num_users] && !item_ids) return fail(SBR_ERR_INVALID_ARGUMENT, "null item_ids");
+    sbr_compressed* c = new (std::nothrow) sbr_compressed();
+    if (!c) return fail(SBR_ERR_INVALID_ARGUMENT, "out of memory");
+    c->num_users = num_users; c->num_items = num_items;
+    c->up_ = user_pointers; c->ii_ = item_ids; c->tt_ = timestamps; c->nnz_ = user_pointers[num_users];
     *out = c;
     return SBR_OK;
 }
 
 size_t sbr_compressed_num_users(const sbr_compressed* c) { return c ? c->num_users : 0; }
 size_t sbr_compressed_num_items(const sbr_compressed* c) { return c ? c->num_items : 0; }
-size_t sbr_compressed_len(const sbr_compressed* c) { return c ? c->item_ids.size() : 0; }
+size_t sbr_compressed_len(const sbr_compressed* c) { return c ? c->nnz_ : 0; }
 
 sbr_status sbr_compressed_borrow(const sbr_compressed* c, const uint64_t** user_pointers, const uint64_t** item_ids,
                                  const uint64_t** timestamps) {
     if (!c) return fail(SBR_ERR_INVALID_ARGUMENT, "null handle");
-    if (user_pointers) *user_pointers = c->user_ptr.data();
-    if (item_ids) *item_ids = c->item_ids.data();
-    if (timestamps) *timestamps = c->timestamps.data();
+    if (user_pointers) *user_pointers = c->up_;
+    if (item_ids) *item_ids = c->ii_;
+    if (timestamps) *timestamps = c->tt_;   /* NULL for a borrowed CSR without timestamps */
     return SBR_OK;
 }
 
@@ -323,7 +363,7 @@ sbr_status sbr_compressed_user_chunks(const sbr_compressed* c, size_t user_id, s
     if (!c || !n) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if (user_id >= c->num_users) return fail(SBR_ERR_INVALID_ARGUMENT, "user id out of range");  // data.rs:278-280
     if (chunk_size == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "chunk_size must be > 0");
-    const size_t len = c->user_ptr[user_id + 1] - c->user_ptr[user_id];
+    const size_t len = c->up_[user_id + 1] - c->up_[user_id];
     size_t idx = 0, k = 0;
     while (idx < len) {  // data.rs:406-432
         const size_t mod = (len - idx) % chunk_size;
@@ -580,11 +620,25 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before using it");
     const double t0 = now_ms();
     const size_t T = (size_t)m->dev.T;
+    // the id stream goes to HBM (narrowed to u32, pinned double buffer) while the host builds the schedule
+    cudaStream_t st = m->stream;
+    cudaEvent_t ev_begin = nullptr;
+    CU(cudaEventCreate(&ev_begin));
+    CU(cudaEventRecord(ev_begin, st));
+    std::string up_err;
+    std::future<sbr_status> up = std::async(std::launch::async, [&]() {
+        cudaSetDevice(g_device);
+        sbr_status r = ensure_uploaded(c, st);
+        if (r) up_err = g_err;
+        return r;
+    });
+    struct Joiner { std::future<sbr_status>& f; cudaEvent_t& e; bool taken = false;
+                    ~Joiner() { if (f.valid()) f.wait(); if (e && !taken) cudaEventDestroy(e); } } joiner{up, ev_begin};
     // sequence_model.rs:76-83: chunk every user, keep len > 2
     std::vector<uint64_t> starts; std::vector<uint32_t> lens;
     uint64_t timesteps = 0;
     for (size_t u = 0; u < c->num_users; ++u) {
-        const size_t b = c->user_ptr[u], len = c->user_ptr[u + 1] - b;
+        const size_t b = c->up_[u], len = c->up_[u + 1] - b;
         size_t idx = 0;
         while (idx < len) {
             const size_t mod = (len - idx) % T;
@@ -625,13 +679,12 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     pl->model = m; pl->nsub = nsub; pl->P = P; pl->n = n;
     pl->timesteps_per_epoch = timesteps;
     pl->stats.host_prepare_ms = t1 - t0;
-    cudaStream_t st = m->stream;
     auto bail = [&](sbr_status r) { delete pl; return r; };
 #define CUP(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return bail(cuda_fail(e__, #expr)); } while (0)
-    for (cudaEvent_t* e : {&pl->ev0, &pl->ev1, &pl->evk0, &pl->evk1}) CUP(cudaEventCreate(e));
-    CUP(cudaEventRecord(pl->ev0, st));
-    s = ensure_uploaded(c, st);
-    if (s) return bail(s);
+    for (cudaEvent_t* e : {&pl->ev1, &pl->evk0, &pl->evk1}) CUP(cudaEventCreate(e));
+    pl->ev0 = ev_begin; joiner.taken = true;
+    s = up.get();
+    if (s) { g_err = up_err; return bail(s); }
     size_t h2d = c->upload_bytes;
     PlanDev& d = pl->dev;
     d.item_ids = c->d_item_ids;
@@ -644,7 +697,17 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     CUP(cudaMalloc(&d.loss_acc, P * sizeof(float)));
     CUP(cudaMalloc(&d.examples, P * sizeof(unsigned long long)));
     d.scratch_stride = train_scratch_floats_per_warp(m->dev);
-    CUP(cudaMalloc(&d.scratch, P * d.scratch_stride * sizeof(float)));
+    {
+        const size_t need = P * d.scratch_stride * sizeof(float);
+        if (!m->scratch_busy) {   // the model keeps one grow-only scratch buffer across fit() calls
+            if (m->scratch_cap < need) {
+                if (m->scratch_cache) { cudaFree(m->scratch_cache); m->scratch_cache = nullptr; m->scratch_cap = 0; }
+                CUP(cudaMalloc(&m->scratch_cache, need));
+                m->scratch_cap = need;
+            }
+            d.scratch = m->scratch_cache; pl->scratch_borrowed = true; m->scratch_busy = true;
+        } else CUP(cudaMalloc(&d.scratch, need));
+    }
     CUP(cudaMemcpyAsync(pl->d_seq_start, starts.data(), nsub * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CUP(cudaMemcpyAsync(pl->d_seq_len, lens.data(), nsub * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CUP(cudaMemcpyAsync(d.order, order.data(), P * n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -827,7 +890,7 @@ sbr_status sbr_model_mrr_score(const sbr_model* m, const sbr_compressed* test, f
     if (flag) return fail(SBR_ERR_INVALID_PREDICTION, "Invalid prediction value: non-finite or not a number.");
     float sum = 0.0f; size_t cnt = 0;  // evaluation.rs:47 mrrs.iter().sum::<f32>() / mrrs.len() as f32, user order
     for (size_t u = 0; u < U; ++u)
-        if (test->user_ptr[u + 1] - test->user_ptr[u] >= 2) { sum += rr[u]; ++cnt; }
+        if (test->up_[u + 1] - test->up_[u] >= 2) { sum += rr[u]; ++cnt; }
     *out = cnt ? sum / (float)cnt : NAN;
     return SBR_OK;
 }
