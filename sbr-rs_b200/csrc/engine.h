@@ -23,6 +23,7 @@ struct ModelDev {
     float4* Bs[8];   // [rows of shard] {b, s1, s2, pad}
     uint32_t gmask;
     int gshift;
+    int hbm_resident; // table + state larger than L2: kernels prefetch rows a few timesteps ahead
     int own_shard;   // >= 0: only this shard is written by init / set_parameter (multi-process); -1: all shards are ours
     float* dense;    // [3][ndense]  w | s1 | s2  (LSTM: W[2D][4][D] then bias[4][D]; EWMA: alpha[D])
     size_t ndense;

@@ -58,6 +58,16 @@ __device__ __forceinline__ void score_and_sample(const ModelDev& m, int lane, co
     }
 }
 
+// Pull an item's row record (and its bias record) towards L2 a couple of timesteps ahead of use: on HBM-resident
+// tables every row visit is a DRAM round trip that nothing else in the warp can hide.
+template <int D>
+__device__ __forceinline__ void prefetch_item(const ModelDev& m, uint32_t id, int lane, int vectors) {
+    const char* rec = reinterpret_cast<const char*>(item_rec(m, id));
+    const int lines = (vectors * D * 4 + 127) / 128;
+    if (lane < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + lane * 128));
+    else if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(bias_rec(m, id)));
+}
+
 // dense (non-embedding) parameter visit by one warp: element i of [w | s1 | s2] arrays of length nd
 template <int D>
 __device__ __forceinline__ void update_dense_vec(float* dense, size_t nd, size_t off, int lane, const float (&g)[VecOf<D>::V],
@@ -84,6 +94,7 @@ __device__ __forceinline__ void update_dense_vec(float* dense, size_t nd, size_t
 template <int D>
 __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl) {
     constexpr int V = VecOf<D>::V;
+    constexpr int kPF = 2;  // prefetch distance in timesteps
     const int lane = threadIdx.x & 31;
     const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= pl.P) return;
@@ -118,6 +129,10 @@ __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl)
             // ---- forward ----
             for (int t = 0; t < Tn; ++t) {
                 const uint32_t in = __ldg(ids + t), out = __ldg(ids + t + 1);
+                if (m.hbm_resident && t + kPF < Tn) {  // rows of timestep t + kPF (the first negative candidate is known in advance)
+                    prefetch_item<D>(m, __ldg(ids + t + kPF + 1), lane, 1);
+                    prefetch_item<D>(m, draw_item(key, step, (uint32_t)(t + kPF), 0u, pl.neg_range), lane, 1);
+                }
                 float x[V], pv[V], qv[V];
                 row_load_cg<D>(item_rec(m, in), lane, x);  // item_embeddings.index(input)
 #pragma unroll
@@ -142,6 +157,11 @@ __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl)
             for (int t = Tn - 1; t >= 0; --t) {
                 const uint32_t in = __ldg(ids + t), out = __ldg(ids + t + 1);
                 const uint32_t neg = NEG[t]; const float g = G_[t];
+                if (m.hbm_resident && t >= kPF) {  // full records (weights + optimizer state) of timestep t - kPF
+                    prefetch_item<D>(m, NEG[t - kPF], lane, m.S);
+                    prefetch_item<D>(m, __ldg(ids + t - kPF + 1), lane, m.S);
+                    prefetch_item<D>(m, __ldg(ids + t - kPF), lane, m.S);
+                }
                 float st[V], dq[V], dh[V], dx[V], gn[V], gp[V];
                 vec_load<D>(S_ + (size_t)t * D, lane, st);
                 vec_load<D>(DQ + (size_t)t * D, lane, dq);
