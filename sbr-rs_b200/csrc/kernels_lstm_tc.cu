@@ -365,7 +365,6 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                 const bool act = t < Tn;
                 float g = 0.0f; uint32_t neg = 0, in = 0, out = 0;
                 if (act) { g = G_[(size_t)t * 128 + r]; neg = NEG[(size_t)t * 128 + r]; in = __ldg(ids + t); out = __ldg(ids + t + 1); }
-                if (t >= 2) prefetch_step(t - 2);   // older timesteps have been evicted to HBM by the forward stream
 #pragma unroll
                 for (int db = 0; db < 4; ++db) {
                     float df[8], di[8], dg[8], dO[8], hp8[8], x8[8];
@@ -424,6 +423,10 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                                  (k > 0 || t < Tmax - 1) ? 1u : 0u);
                     mma_commit(mbar + tile);
                 }
+                // Next timestep's activations: the forward stream evicted them to HBM (296 tiles x 4 MB); fetch them into L2
+                // now, one MMA + three row visits ahead of their use -- early enough for DRAM latency, late enough that
+                // the other tiles' traffic does not evict them again (the whole L2 turns over in about two timesteps).
+                if (t >= 1) prefetch_step(t - 1);
                 // overlap with the MMAs: the two visits that need only h_t  (t descending: E[neg], E[out], ..)
                 __syncwarp();
                 coop_update(m, neg, act, lane, stage_b, 1.0f, o);
