@@ -44,55 +44,66 @@ __device__ __forceinline__ void ewma_represent(const ModelDev& m, const uint32_t
     vec_store<D>(out, lane, s);
 }
 
+// LSTM state after a history; lane l owns units l*V..l*V+V-1 (D < 32: lane l < D owns unit l).  zbuf: 2*D floats of
+// shared memory private to the calling warp.
 template <int D>
-__device__ __forceinline__ void lstm_represent(const ModelDev& m, const uint32_t* ids, int n, int lane, float* out) {
-    static_assert(D <= 32, "warp-per-user LSTM inference supports D <= 32");
-    const size_t RS = (size_t)m.S * D;
-    const bool act = lane < D;
-    const int ld = act ? lane : 0;
+__device__ __forceinline__ void lstm_represent(const ModelDev& m, const uint32_t* ids, int n, int lane, float* out, float* zbuf) {
+    constexpr int V = VecOf<D>::V;
     const float* W = m.dense; const float* B = m.dense + (size_t)2 * D * 4 * D;
     const bool coupled = m.variant == 1;
-    float h = 0.0f, c = 0.0f;
+    float h[V], c[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { h[v] = 0.0f; c[v] = 0.0f; }
     for (int t = 0; t < n; ++t) {
         const uint32_t in = ids ? __ldg(ids + t) : 0u;
-        float x[1];
+        float x[V], pre[4][V];
         row_load_cg<D>(item_rec(m, in), lane, x);
-        float pre[4];
+        vec_store<D>(zbuf, lane, h); vec_store<D>(zbuf + D, lane, x);
+        __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) pre[q] = __ldcg(B + q * D + ld);
+        for (int q = 0; q < 4; ++q) row_load_cg<D>(B + q * D, lane, pre[q]);
         for (int k = 0; k < 2 * D; ++k) {
-            const float zk = k < D ? __shfl_sync(kFull, h, k) : __shfl_sync(kFull, x[0], k - D);
-            const float* Wk = W + (size_t)k * 4 * D + ld;
+            const float zk = zbuf[k];
+            float w[V];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) pre[q] = fmaf(zk, __ldcg(Wk + q * D), pre[q]);
+            for (int q = 0; q < 4; ++q) {
+                row_load_cg<D>(W + ((size_t)k * 4 + q) * D, lane, w);
+#pragma unroll
+                for (int v = 0; v < V; ++v) pre[q][v] = fmaf(zk, w[v], pre[q][v]);
+            }
         }
-        const float f = sigmoidf_(pre[0]);
-        const float ig = coupled ? 1.0f - f : sigmoidf_(pre[1]);
-        const float gg = tanhf(pre[2]);
-        const float og = sigmoidf_(pre[3]);
-        c = act ? f * c + ig * gg : 0.0f;
-        h = act ? og * tanhf(c) : 0.0f;
+        __syncwarp();
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const float f = sigmoidf_(pre[0][v]);
+            const float ig = coupled ? 1.0f - f : sigmoidf_(pre[1][v]);
+            const float gg = tanhf(pre[2][v]);
+            const float og = sigmoidf_(pre[3][v]);
+            c[v] = f * c[v] + ig * gg;
+            h[v] = og * tanhf(c[v]);
+        }
     }
-    if (act) out[lane] = h;
+    vec_store<D>(out, lane, h);
 }
 
 template <int D>
-__device__ __forceinline__ void represent(const ModelDev& m, const uint32_t* ids, int n, int lane, float* out) {
+__device__ __forceinline__ void represent(const ModelDev& m, const uint32_t* ids, int n, int lane, float* out, float* zbuf) {
     if (n == 0) { ids = nullptr; n = 1; }  // sequence_model.rs:197-200: hidden_states[0] with the default index 0
     if (m.model == MODEL_EWMA) ewma_represent<D>(m, ids, n, lane, out);
-    else if constexpr (D <= 32) lstm_represent<D>(m, ids, n, lane, out);
+    else lstm_represent<D>(m, ids, n, lane, out, zbuf);
 }
 
 template <int D>
 __global__ void __launch_bounds__(128) user_rep_kernel(ModelDev m, const uint64_t* __restrict__ ptr,
                                                        const uint32_t* __restrict__ ids, size_t num_users, float* out) {
+    __shared__ float zb[4][2 * D];
     const int lane = threadIdx.x & 31;
     const size_t u = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (u >= num_users) return;
     uint64_t b = ptr[u], e = ptr[u + 1];
     uint64_t n = e - b;
     if (n > (uint64_t)m.T) { b = e - m.T; n = m.T; }  // sequence_model.rs:188
-    represent<D>(m, ids + b, (int)n, lane, out + u * D);
+    represent<D>(m, ids + b, (int)n, lane, out + u * D, zb[threadIdx.x >> 5]);
 }
 
 // predict_single: bias + dot(user, row).  One thread per item, 16-byte loads.
@@ -128,6 +139,7 @@ __global__ void __launch_bounds__(256) mrr_kernel(ModelDev m, const uint64_t* __
                                                   const uint32_t* __restrict__ ids, size_t num_users, float* pred_all,
                                                   float* rr, int* nonfinite) {
     __shared__ float user[D];
+    __shared__ float zb[2 * D];
     __shared__ unsigned int cnt;
     float* pred = pred_all + (size_t)blockIdx.x * m.N;
     for (size_t u = blockIdx.x; u < num_users; u += gridDim.x) {
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(256) mrr_kernel(ModelDev m, const uint64_t* __
         const uint32_t test_item = ids[e - 1];                                   // :25
         uint64_t hb = b, hn = len - 1;                                           // :24 all but the last
         if (hn > (uint64_t)m.T) { hb = (e - 1) - m.T; hn = m.T; }
-        if (threadIdx.x < 32) represent<D>(m, ids + hb, (int)hn, threadIdx.x, user);  // :27
+        if (threadIdx.x < 32) represent<D>(m, ids + hb, (int)hn, threadIdx.x, user, zb);  // :27
         if (threadIdx.x == 0) cnt = 0;
         __syncthreads();
         for (uint32_t j = threadIdx.x; j < m.N; j += blockDim.x) {               // :16,28 all items

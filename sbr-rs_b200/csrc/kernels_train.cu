@@ -452,6 +452,209 @@ __global__ void __launch_bounds__(WPC * 32) lstm_train_kernel(ModelDev m, PlanDe
     }
 }
 
+
+// =====================================================================================================
+// LSTM, generic-width FFMA path, D in {64, 128, 256} (BASELINE configs C3, C5).  One warp == one partition; lane l owns
+// units l*V .. l*V+V-1 (V = D/32).  The weights (8*D*D floats: 131 KB .. 2 MB) do not fit shared memory, so they are read
+// from L2 (ld.cg: they are Hogwild-shared) as coalesced V-float vectors, three passes per timestep (gates, dz, dW).
+// The dense optimizer step is applied per sequence by the warp itself, rows of W at a time, exactly like the
+// reference (one optimizer.step per sub-sequence, sequence_model.rs:163-169).  Correct and parity-tested; the
+// tensor-core tile kernel (kernels_lstm_tc.cu) is the fast path and currently covers D = 32 only.
+// scratch per warp: [T][8][D] = x,h,c,f,i,g,o,dq ; then G[T], NEG[T]
+// =====================================================================================================
+template <int D, int WPC>
+__global__ void __launch_bounds__(WPC * 32) lstm_wide_train_kernel(ModelDev m, PlanDev pl) {
+    constexpr int V = D / 32, NK = 2 * D;
+    constexpr int KC = 64 / (4 * V) > 0 ? 64 / (4 * V) : 1;   // rows of W per dW chunk: 4*V*KC = 64 accumulators
+    extern __shared__ float smem_w[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t p = blockIdx.x * WPC + warp;
+    if (p >= pl.P) return;
+    float* zbuf = smem_w + warp * (NK + NK);       // [NK] z = [h, x]
+    float* dzbuf = zbuf + NK;                      // [NK] dz
+    const int T = m.T;
+    const size_t nd = m.ndense;
+    const bool coupled = m.variant == 1;
+    float* ws = pl.scratch + (size_t)p * pl.scratch_stride;
+    float* G_ = ws + (size_t)T * 8 * D; uint32_t* NEG = reinterpret_cast<uint32_t*>(G_ + T);
+    auto slot = [&](int t, int which) { return ws + ((size_t)t * 8 + which) * D; };
+    enum { SX = 0, SH = 1, SC = 2, SF = 3, SI = 4, SG = 5, SO = 6, SDQ = 7 };
+    const float* W = m.dense; const float* Bv = m.dense + (size_t)NK * 4 * D;
+
+    XorShift rng = pl.rng[p];
+    const uint64_t key = pl.keys[p];
+    uint64_t step = pl.step_ctr[p];
+    uint32_t* ord = pl.order + (size_t)p * pl.n;
+    float loss_acc = 0.0f; unsigned long long ex = 0;
+    OptCfg o; o.lr = m.lr; o.l2 = m.l2; o.adam = m.opt == 1; o.c1 = 1.0f; o.c2 = 1.0f;
+
+    for (int ep = 0; ep < pl.epochs; ++ep) {
+        if (lane == 0) shuffle_partition(ord, pl.n, rng);
+        __syncwarp();
+        for (uint32_t it = 0; it < pl.n; ++it, ++step) {
+            const uint32_t sq = ord[it];
+            const uint32_t* ids = pl.item_ids + pl.seq_start[sq];
+            const int Tn = (int)pl.seq_len[sq] - 1;
+            adam_corrections(o, pl.adam_t0 + step * pl.P + p + 1);
+            float h[V], c[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) { h[v] = 0.0f; c[v] = 0.0f; }
+            float loss_seq = 0.0f;
+            // ---------------- forward ----------------
+            for (int t = 0; t < Tn; ++t) {
+                const uint32_t in = __ldg(ids + t), out = __ldg(ids + t + 1);
+                float x[V], pre[4][V], pv[V], qv[V];
+                row_load_cg<D>(item_rec(m, in), lane, x);
+                vec_store<D>(zbuf, lane, h); vec_store<D>(zbuf + D, lane, x);
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) row_load_cg<D>(Bv + q * D, lane, pre[q]);
+                for (int k = 0; k < NK; ++k) {
+                    const float zk = zbuf[k];
+                    float w[V];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        row_load_cg<D>(W + ((size_t)k * 4 + q) * D, lane, w);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) pre[q][v] = fmaf(zk, w[v], pre[q][v]);
+                    }
+                }
+                __syncwarp();
+                float f[V], ig[V], gg[V], og[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    f[v] = sigmoidf_(pre[0][v]);
+                    ig[v] = coupled ? 1.0f - f[v] : sigmoidf_(pre[1][v]);
+                    gg[v] = tanhf(pre[2][v]);
+                    og[v] = sigmoidf_(pre[3][v]);
+                    c[v] = f[v] * c[v] + ig[v] * gg[v];
+                    h[v] = og[v] * tanhf(c[v]);
+                }
+                vec_store<D>(slot(t, SX), lane, x); vec_store<D>(slot(t, SH), lane, h); vec_store<D>(slot(t, SC), lane, c);
+                vec_store<D>(slot(t, SF), lane, f); vec_store<D>(slot(t, SI), lane, ig); vec_store<D>(slot(t, SG), lane, gg);
+                vec_store<D>(slot(t, SO), lane, og);
+                uint32_t neg; float pos, ngs;
+                score_and_sample<D>(m, lane, h, out, key, step, (uint32_t)t, pl.neg_range, pv, qv, neg, pos, ngs);
+                StepOut lo = pair_loss(m.loss, pos, ngs);
+                loss_seq += lo.loss;
+                float dq[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) dq[v] = lo.g * (qv[v] - pv[v]);
+                vec_store<D>(slot(t, SDQ), lane, dq);
+                if (lane == 0) { G_[t] = lo.g; NEG[t] = neg; }
+            }
+            __syncwarp();
+            // ---------------- backward ----------------
+            float dh_rec[V], dc_rec[V], db[4][V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) { dh_rec[v] = 0.0f; dc_rec[v] = 0.0f; db[0][v] = db[1][v] = db[2][v] = db[3][v] = 0.0f; }
+            for (int t = Tn - 1; t >= 0; --t) {
+                const uint32_t in = __ldg(ids + t), out = __ldg(ids + t + 1);
+                const uint32_t neg = NEG[t]; const float g = G_[t];
+                float ht[V], ct[V], cp[V], f[V], ig[V], gg[V], og[V], dq[V], del[4][V];
+                vec_load<D>(slot(t, SH), lane, ht); vec_load<D>(slot(t, SC), lane, ct); vec_load<D>(slot(t, SF), lane, f);
+                vec_load<D>(slot(t, SI), lane, ig); vec_load<D>(slot(t, SG), lane, gg); vec_load<D>(slot(t, SO), lane, og);
+                vec_load<D>(slot(t, SDQ), lane, dq);
+                if (t > 0) vec_load<D>(slot(t - 1, SC), lane, cp);
+                else {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) cp[v] = 0.0f;
+                }
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const float tc = tanhf(ct[v]);
+                    const float dh = dh_rec[v] + dq[v];
+                    const float d_o = dh * tc;
+                    const float dc = dc_rec[v] + dh * og[v] * (1.0f - tc * tc);
+                    float d_f = dc * cp[v], d_i = dc * gg[v];
+                    const float d_g = dc * ig[v];
+                    dc_rec[v] = dc * f[v];
+                    if (coupled) { d_f -= d_i; d_i = 0.0f; }
+                    del[0][v] = d_f * f[v] * (1.0f - f[v]);
+                    del[1][v] = coupled ? 0.0f : d_i * ig[v] * (1.0f - ig[v]);
+                    del[2][v] = d_g * (1.0f - gg[v] * gg[v]);
+                    del[3][v] = d_o * og[v] * (1.0f - og[v]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) db[q][v] += del[q][v];
+                }
+                // deltas replace the gates in scratch (consumed by the dW pass)
+                vec_store<D>(slot(t, SF), lane, del[0]); vec_store<D>(slot(t, SI), lane, del[1]);
+                vec_store<D>(slot(t, SG), lane, del[2]); vec_store<D>(slot(t, SO), lane, del[3]);
+                // dz[k] = sum_{q,d} del[q][d] W[k][q][d]: 64 rows of W per multi-reduce
+                for (int kb = 0; kb < NK; kb += 64) {
+                    float part[64];
+#pragma unroll
+                    for (int kk = 0; kk < 64; ++kk) {
+                        float a0 = 0.0f, w[V];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            row_load_cg<D>(W + ((size_t)(kb + kk) * 4 + q) * D, lane, w);
+#pragma unroll
+                            for (int v = 0; v < V; ++v) a0 = fmaf(del[q][v], w[v], a0);
+                        }
+                        part[2 * (kk % 32) + kk / 32] = a0;
+                    }
+                    warp_multi_reduce<64>(part, lane);
+                    dzbuf[kb + lane] = part[0]; dzbuf[kb + 32 + lane] = part[1];
+                }
+                __syncwarp();
+                float dx[V];
+                vec_load<D>(dzbuf, lane, dh_rec); vec_load<D>(dzbuf + D, lane, dx);
+                __syncwarp();
+                float gn[V], gp[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) { gn[v] = g * ht[v]; gp[v] = -g * ht[v]; }
+                update_row<D>(item_rec(m, neg), lane, gn, o);
+                update_row<D>(item_rec(m, out), lane, gp, o);
+                update_row<D>(item_rec(m, in), lane, dx, o);
+                if (lane == 0) {
+                    update_bias(bias_rec(m, neg), g, o);
+                    update_bias(bias_rec(m, out), -g, o);
+                }
+                __syncwarp();
+            }
+            // ---------------- dense step: dW = sum_t z_t^T delta_t, KC rows of W at a time, applied in place ----------------
+            for (int kb = 0; kb < NK; kb += KC) {
+                float acc[KC][4][V];
+#pragma unroll
+                for (int kk = 0; kk < KC; ++kk)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int v = 0; v < V; ++v) acc[kk][q][v] = 0.0f;
+                const bool hpart = kb < D;
+                const int off = hpart ? kb : kb - D;
+                for (int t = Tn - 1; t >= 0; --t) {
+                    if (hpart && t == 0) continue;   // h_{-1} = 0
+                    const float* zs = (hpart ? slot(t - 1, SH) : slot(t, SX)) + off;
+                    float dl[4][V];
+                    vec_load<D>(slot(t, SF), lane, dl[0]); vec_load<D>(slot(t, SI), lane, dl[1]);
+                    vec_load<D>(slot(t, SG), lane, dl[2]); vec_load<D>(slot(t, SO), lane, dl[3]);
+#pragma unroll
+                    for (int kk = 0; kk < KC; ++kk) {
+                        const float zk = zs[kk];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+#pragma unroll
+                            for (int v = 0; v < V; ++v) acc[kk][q][v] = fmaf(zk, dl[q][v], acc[kk][q][v]);
+                    }
+                }
+#pragma unroll
+                for (int kk = 0; kk < KC; ++kk)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) update_dense_vec<D>(m.dense, nd, ((size_t)(kb + kk) * 4 + q) * D, lane, acc[kk][q], o);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) update_dense_vec<D>(m.dense, nd, (size_t)NK * 4 * D + q * D, lane, db[q], o);
+            loss_acc += loss_seq; ex += (unsigned long long)Tn;
+        }
+    }
+    if (lane == 0) {
+        pl.rng[p] = rng; pl.step_ctr[p] = step;
+        pl.loss_acc[p] += loss_acc; pl.examples[p] += ex;
+    }
+}
+
 template <int D, int WPC>
 constexpr size_t lstm_smem_bytes() { return sizeof(float4) * (2 * (2 * D) * D + 2 * D) + sizeof(float) * WPC * 2 * D; }
 
@@ -466,8 +669,8 @@ bool train_supported(const ModelDev& m, const char** why) {
         *why = "EWMA embedding_dim must be one of 16, 32, 64, 128, 256";
         return false;
     }
-    if (m.D == 16 || m.D == 32) return true;
-    *why = "LSTM embedding_dim must be 16 or 32 on the FFMA path (larger dims: tensor-core path, not built yet)";
+    if (m.D == 16 || m.D == 32 || m.D == 64 || m.D == 128 || m.D == 256) return true;
+    *why = "LSTM embedding_dim must be one of 16, 32, 64, 128, 256";
     return false;
 }
 
@@ -480,6 +683,7 @@ size_t train_scratch_floats_per_warp(const ModelDev& m) {
 int train_auto_partitions(const ModelDev& m, int num_sms) {
     // EWMA / FFMA LSTM: resident warps per SM (registers / shared memory); tensor-core LSTM: 2 tiles of 128 per SM
     if (m.model == MODEL_LSTM && m.D == 32) return num_sms * 256;
+    if (m.model == MODEL_LSTM && m.D > 32) return num_sms * 8;
     int per_sm = m.model == MODEL_EWMA ? (m.D <= 64 ? 32 : 16) : 16;
     return num_sms * per_sm;
 }
@@ -521,6 +725,13 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
             *err = cudaFuncSetAttribute(lstm_train_kernel<16, kLstmWPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (*err != cudaSuccess) return 0;
             lstm_train_kernel<16, kLstmWPC><<<grid, block, smem, st>>>(m, p);
+        } else if (m.D == 64 || m.D == 128 || m.D == 256) {
+            constexpr int WPCW = 4;
+            dim3 blockw(WPCW * 32), gridw((p.P + WPCW - 1) / WPCW);
+            const size_t smem = sizeof(float) * WPCW * 4 * m.D;
+            if (m.D == 64) lstm_wide_train_kernel<64, WPCW><<<gridw, blockw, smem, st>>>(m, p);
+            else if (m.D == 128) lstm_wide_train_kernel<128, WPCW><<<gridw, blockw, smem, st>>>(m, p);
+            else lstm_wide_train_kernel<256, WPCW><<<gridw, blockw, smem, st>>>(m, p);
         } else { *err = cudaErrorInvalidValue; return 0; }
     }
     *err = cudaGetLastError();

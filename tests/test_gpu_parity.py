@@ -59,6 +59,10 @@ CASES = [
     ("lstm", 32, "bpr", "adam", "coupled"),
     ("lstm", 16, "warp", "adam", "normal"),
     ("lstm", 16, "hinge", "adagrad", "coupled"),
+    ("lstm", 64, "hinge", "adam", "normal"),      # config C3 shape (generic-width kernel)
+    ("lstm", 64, "bpr", "adagrad", "coupled"),
+    ("lstm", 128, "warp", "adagrad", "normal"),
+    ("lstm", 256, "warp", "adagrad", "normal"),   # config C5 shape
 ]
 
 
@@ -71,6 +75,15 @@ def test_fit_matches_oracle_single_thread(pkg, oracle, kind, D, loss, optimizer,
     ptr, ids = random_csr(rng, 30, N, 1, 40)  # ragged: lengths 1..40 => dropped (<=2), short and full chunks
     gm, om = make_pair(pkg, oracle, kind, N, T, D, loss=loss, optimizer=optimizer, variant=variant, lr=0.05, l2=1e-3,
                        epochs=2, threads=1, scale=0.3)
+    if kind == "lstm" and D >= 64:
+        # Wide models: thousands of weights see gradients of ~1e-9, where Adagrad's first step lr*g/(1e-10+|g|) (and
+        # Adam's) turns 1-ulp differences into O(lr) jumps (measured: single elements off by 2e-4 after ONE step, all
+        # others within 1e-5).  Start the second-moment state at 1 on both sides so steps are smooth in g.
+        st = ".s2" if optimizer == "adam" else ".s1"
+        for n in om.param_names():
+            ones = np.ones(len(om.param(n)), dtype=np.float32)
+            gm.set_parameter(n + st, ones)
+            om.param(n + st)[:] = 1.0
     data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
     gl = gm.fit(data)
     rc, ol = om.fit(ptr, ids)
@@ -125,7 +138,7 @@ def test_inference_matches_oracle(pkg, oracle):
     """user_representation / predict / mrr_score (sequence_model.rs:180-233, evaluation.rs:12-48)."""
     rng = np.random.default_rng(3)
     N, T = 500, 16
-    for kind, D in (("lstm", 32), ("lstm", 16), ("ewma", 32), ("ewma", 128)):
+    for kind, D in (("lstm", 32), ("lstm", 16), ("lstm", 64), ("lstm", 256), ("ewma", 32), ("ewma", 128)):
         gm, om = make_pair(pkg, oracle, kind, N, T, D, scale=0.3)
         for n in (0, 1, 5, 16, 40):  # empty, shorter than T, exactly T, longer than T (last T used)
             hist = rng.integers(0, N, size=n).astype(np.uint64)
