@@ -226,6 +226,12 @@ def main():
     if rank == 0:
         peak, peak_kind = peaks()
         per_launch_bytes = A_TRAIN_BYTES_PER_TIMESTEP * (timesteps / max(launches, 1))
+        traffic = None  # DRAM bytes per launch from the committed ncu --set full capture (scaled to this launch size)
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_launch"] * (steps_done / tj["seqs_per_launch"])
         per_launch_ms = kernel_ms / max(launches, 1)
         achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
         out = {
@@ -243,7 +249,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "lstm_tc_train_kernel<2> (tcgen05 tile kernel)",
+                         "traffic": traffic, "peak_kind": peak_kind, "kernel": "lstm_tc_train_kernel<2> (tcgen05 tile kernel)",
                          "algorithmic_bytes_per_timestep": A_TRAIN_BYTES_PER_TIMESTEP},
         }
         if not args.no_cpu_baseline:
