@@ -443,7 +443,7 @@ sbr_status sbr_hyper_build(sbr_hyperparameters* hp, sbr_model** out) {
     d.N = (uint32_t)h.num_items; d.D = (int)h.embedding_dim; d.T = (int)h.max_sequence_length;
     d.S = h.optimizer == SBR_OPTIMIZER_ADAM ? 3 : 2;
     d.lr = h.learning_rate; d.l2 = h.l2_penalty;
-    d.hbm_resident = (size_t)d.N * d.S * d.D * sizeof(float) > (size_t)96 << 20;
+    d.hbm_resident = (size_t)d.N * d.S * d.D * sizeof(float) > (size_t)96 << 20 && !getenv("SBR_NO_PREFETCH");
     d.ndense = h.model == MODEL_LSTM ? (size_t)2 * d.D * 4 * d.D + 4 * d.D : (size_t)d.D;
     const char* why = nullptr;
     if (!train_supported(d, &why)) { delete m; return fail(SBR_ERR_UNSUPPORTED, why); }

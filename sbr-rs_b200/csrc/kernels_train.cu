@@ -62,6 +62,9 @@ __device__ __forceinline__ void score_and_sample(const ModelDev& m, int lane, co
 // tables every row visit is a DRAM round trip that nothing else in the warp can hide.
 template <int D>
 __device__ __forceinline__ void prefetch_item(const ModelDev& m, uint32_t id, int lane, int vectors) {
+    // local shards only: prefetch.global.L2 on a peer (NVLink) address stalls for tens of microseconds (measured:
+    // 25x slowdown of the whole kernel), and the peer's L2 is not ours to fill anyway
+    if (m.own_shard >= 0 && (int)(id & m.gmask) != m.own_shard) return;
     const char* rec = reinterpret_cast<const char*>(item_rec(m, id));
     const int lines = (vectors * D * 4 + 127) / 128;
     if (lane < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + lane * 128));
@@ -126,21 +129,43 @@ __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl)
             for (int v = 0; v < V; ++v) { a[v] = sigmoidf_(al[v]); s[v] = 0.0f; }
 
             float loss_seq = 0.0f;
-            // ---- forward ----
-            for (int t = 0; t < Tn; ++t) {
+            // ---- forward: the three rows of timestep t+1 (input, target, first negative candidate -- all known in
+            // advance) are loaded while timestep t is being computed, so a row visit costs one exposed round trip at
+            // most, local HBM or a peer GPU over NVLink alike ----
+            float xn[V], pn[V], qn[V], bpn = 0.0f, bqn = 0.0f; uint32_t candn = 0;
+            auto issue_rows = [&](int t) {
                 const uint32_t in = __ldg(ids + t), out = __ldg(ids + t + 1);
-                if (m.hbm_resident && t + kPF < Tn) {  // rows of timestep t + kPF (the first negative candidate is known in advance)
+                candn = draw_item(key, step, (uint32_t)t, 0u, pl.neg_range);
+                row_load_cg<D>(item_rec(m, in), lane, xn);     // item_embeddings.index(input)
+                row_load_cg<D>(item_rec(m, out), lane, pn);
+                row_load_cg<D>(item_rec(m, candn), lane, qn);
+                bpn = __ldcg(reinterpret_cast<const float*>(bias_rec(m, out)));
+                bqn = __ldcg(reinterpret_cast<const float*>(bias_rec(m, candn)));
+            };
+            if (Tn > 0) issue_rows(0);
+            for (int t = 0; t < Tn; ++t) {
+                float x[V], pv[V], qv[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) { x[v] = xn[v]; pv[v] = pn[v]; qv[v] = qn[v]; }
+                const float bp = bpn; float bq = bqn; uint32_t neg = candn;
+                if (m.hbm_resident && t + kPF < Tn) {
                     prefetch_item<D>(m, __ldg(ids + t + kPF + 1), lane, 1);
                     prefetch_item<D>(m, draw_item(key, step, (uint32_t)(t + kPF), 0u, pl.neg_range), lane, 1);
                 }
-                float x[V], pv[V], qv[V];
-                row_load_cg<D>(item_rec(m, in), lane, x);  // item_embeddings.index(input)
+                if (t + 1 < Tn) issue_rows(t + 1);
 #pragma unroll
                 for (int v = 0; v < V; ++v) s[v] = t == 0 ? x[v] : a[v] * s[v] + (1.0f - a[v]) * x[v];
                 vec_store<D>(S_ + (size_t)t * D, lane, s);
                 vec_store<D>(X_ + (size_t)t * D, lane, x);
-                uint32_t neg; float pos, ngs;
-                score_and_sample<D>(m, lane, s, out, key, step, (uint32_t)t, pl.neg_range, pv, qv, neg, pos, ngs);
+                const float pos = warp_dot<D>(s, pv) + bp;
+                float ngs = warp_dot<D>(s, qv) + bq;
+                if (m.loss == 2) {  // WARP: further candidates only while the current one is not a violator (sequence_model.rs:58-65)
+                    for (int j = 1; j < 5 && !(1.0f - pos + ngs > 0.0f); ++j) {
+                        neg = draw_item(key, step, (uint32_t)t, (uint32_t)j, pl.neg_range);
+                        row_load_cg<D>(item_rec(m, neg), lane, qv);
+                        ngs = warp_dot<D>(s, qv) + __ldcg(reinterpret_cast<const float*>(bias_rec(m, neg)));
+                    }
+                }
                 StepOut lo = pair_loss(m.loss, pos, ngs);
                 loss_seq += lo.loss;
                 float dq[V];
@@ -161,6 +186,16 @@ __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl)
                     prefetch_item<D>(m, NEG[t - kPF], lane, m.S);
                     prefetch_item<D>(m, __ldg(ids + t - kPF + 1), lane, m.S);
                     prefetch_item<D>(m, __ldg(ids + t - kPF), lane, m.S);
+                }
+                // when the three rows are distinct their records are loaded together (one round trip instead of three)
+                const bool distinct = neg != out && neg != in && out != in;
+                float* rn = item_rec(m, neg); float* ro = item_rec(m, out); float* ri = item_rec(m, in);
+                float wn[V], gnn[V], wo[V], goo[V], wi[V], gii[V], vn[V], vo[V], vi[V];
+                if (distinct) {
+                    row_load_cg<D>(rn, lane, wn); row_load_cg<D>(rn + D, lane, gnn);
+                    row_load_cg<D>(ro, lane, wo); row_load_cg<D>(ro + D, lane, goo);
+                    row_load_cg<D>(ri, lane, wi); row_load_cg<D>(ri + D, lane, gii);
+                    if (o.adam) { row_load_cg<D>(rn + 2 * D, lane, vn); row_load_cg<D>(ro + 2 * D, lane, vo); row_load_cg<D>(ri + 2 * D, lane, vi); }
                 }
                 float st[V], dq[V], dh[V], dx[V], gn[V], gp[V];
                 vec_load<D>(S_ + (size_t)t * D, lane, st);
@@ -183,9 +218,26 @@ __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl)
                 }
 #pragma unroll
                 for (int v = 0; v < V; ++v) { gn[v] = g * st[v]; gp[v] = -g * st[v]; }
-                update_row<D>(item_rec(m, neg), lane, gn, o);
-                update_row<D>(item_rec(m, out), lane, gp, o);
-                update_row<D>(item_rec(m, in), lane, dx, o);
+                if (distinct) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        if (!o.adam) {
+                            adagrad_elem(wn[v], gnn[v], gn[v], o.lr, o.l2); adagrad_elem(wo[v], goo[v], gp[v], o.lr, o.l2);
+                            adagrad_elem(wi[v], gii[v], dx[v], o.lr, o.l2);
+                        } else {
+                            adam_elem(wn[v], gnn[v], vn[v], gn[v], o); adam_elem(wo[v], goo[v], vo[v], gp[v], o);
+                            adam_elem(wi[v], gii[v], vi[v], dx[v], o);
+                        }
+                    }
+                    row_store_cg<D>(rn, lane, wn); row_store_cg<D>(rn + D, lane, gnn);
+                    row_store_cg<D>(ro, lane, wo); row_store_cg<D>(ro + D, lane, goo);
+                    row_store_cg<D>(ri, lane, wi); row_store_cg<D>(ri + D, lane, gii);
+                    if (o.adam) { row_store_cg<D>(rn + 2 * D, lane, vn); row_store_cg<D>(ro + 2 * D, lane, vo); row_store_cg<D>(ri + 2 * D, lane, vi); }
+                } else {  // repeated item inside the timestep: strictly sequential visits
+                    update_row<D>(rn, lane, gn, o);
+                    update_row<D>(ro, lane, gp, o);
+                    update_row<D>(ri, lane, dx, o);
+                }
                 if (lane == 0) {
                     update_bias(bias_rec(m, neg), g, o);
                     update_bias(bias_rec(m, out), -g, o);
