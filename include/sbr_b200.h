@@ -139,6 +139,14 @@ void sbr_model_free(sbr_model* m);
  * with sbr_model_ipc_export, the host program all-gathers them in rank order (any transport), and every rank calls
  * sbr_model_ipc_attach.  Ranks then call sbr_model_fit concurrently, each on its own users' interactions. */
 sbr_status sbr_hyper_shard(sbr_hyperparameters* h, int rank, int world);   /* world in {1,2,4,8} */
+/* Parallelism::Synchronous across GPUs (EWMA, BPR/hinge): round-synchronous schedule; per round the ranks exchange
+ * requested item ids, the rows, and the gradient rows with NCCL grouped send/recv (all-to-all over NVLink) and the
+ * owners apply the optimizer to their own shard, so random table access never leaves a GPU's HBM -- the mode for
+ * catalogues too large for one GPU.  Rank 0 creates the 128-byte NCCL id, the host program broadcasts it, every rank
+ * calls sbr_dist_init once per process; models are built with sbr_hyper_shard(rank, world) (no IPC attach needed). */
+sbr_status sbr_dist_unique_id(uint8_t out[128]);
+sbr_status sbr_dist_init(int rank, int world, const uint8_t id[128]);
+void sbr_dist_finalize(void);
 /* Same sharded addressing with all shards in this process / on this device (used by single-GPU tests). */
 sbr_status sbr_hyper_virtual_shards(sbr_hyperparameters* h, int shards);
 size_t sbr_model_ipc_handle_size(void);

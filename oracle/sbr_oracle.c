@@ -310,15 +310,15 @@ static inline void adam_elem(float* w, float* mm, float* vv, float g, float lr, 
     *w -= lr / (sqrtf(vhat) + eps) * mhat;
 }
 
-static void apply_update(sbo_model* m, sbo_ws* w) {
+static void adam_coeffs(const sbo_model* m, uint64_t t, float* c1, float* c2) {
+    *c1 = 1.0f; *c2 = 1.0f;
+    if (m->h.optimizer == SBO_OPT_ADAM) { *c1 = 1.0f - powf(0.9f, (float)t); *c2 = 1.0f - powf(0.999f, (float)t); }
+}
+
+/* sparse rows: one update per recorded (row, grad) entry, in order, duplicates NOT merged [wyrm-recalled] */
+static void apply_sparse(sbo_model* m, const sbo_ws* w, float c1, float c2) {
     const size_t D = m->D; const float lr = m->h.learning_rate, l2 = m->h.l2_penalty;
     const int adam = m->h.optimizer == SBO_OPT_ADAM;
-    float c1 = 1, c2 = 1;
-    uint64_t t = ++m->num_updates; /* per-parameter num_updates, one per step() [wyrm-recalled] */
-    if (adam) {
-        c1 = 1.0f - powf(0.9f, (float)t); c2 = 1.0f - powf(0.999f, (float)t);
-    }
-    /* sparse rows: one update per recorded (row, grad) entry, in order, duplicates NOT merged */
     for (size_t e = 0; e < w->nrows; ++e) {
         size_t r = w->rows[e]; const float* g = w->grads + e * D;
         float* wv = m->E + r * D; float* s1 = m->E_s1 + r * D; float* s2 = m->E_s2 + r * D;
@@ -332,11 +332,24 @@ static void apply_update(sbo_model* m, sbo_ws* w) {
         if (adam) adam_elem(m->b + r, m->b_s1 + r, m->b_s2 + r, w->bgrads[e], lr, l2, c1, c2);
         else adagrad_elem(m->b + r, m->b_s1 + r, w->bgrads[e], lr, l2);
     }
-    /* dense parameters (LSTM weights+biases / alpha): every element, every step */
+}
+
+/* dense parameters (LSTM weights+biases / alpha): every element, every step */
+static void apply_dense(sbo_model* m, const float* grad, float c1, float c2) {
+    const float lr = m->h.learning_rate, l2 = m->h.l2_penalty;
+    const int adam = m->h.optimizer == SBO_OPT_ADAM;
     for (size_t i = 0; i < m->ndense; ++i) {
-        if (adam) adam_elem(m->dense + i, m->dense_s1 + i, m->dense_s2 + i, w->dense_grad[i], lr, l2, c1, c2);
-        else adagrad_elem(m->dense + i, m->dense_s1 + i, w->dense_grad[i], lr, l2);
+        if (adam) adam_elem(m->dense + i, m->dense_s1 + i, m->dense_s2 + i, grad[i], lr, l2, c1, c2);
+        else adagrad_elem(m->dense + i, m->dense_s1 + i, grad[i], lr, l2);
     }
+}
+
+static void apply_update(sbo_model* m, sbo_ws* w) {
+    float c1, c2;
+    uint64_t t = ++m->num_updates; /* per-parameter num_updates, one per step() [wyrm-recalled] */
+    adam_coeffs(m, t, &c1, &c2);
+    apply_sparse(m, w, c1, c2);
+    apply_dense(m, w->dense_grad, c1, c2);
 }
 
 /* ---- recurrent cells ---- */
@@ -518,9 +531,20 @@ static void* run_partition(void* arg) {
             uint32_t s = pt->order[i];
             float l = step_ws(m, pt->ws, pt->item_ids + pt->starts[s], pt->lens[s], key, step++, NULL, 1);
             loss_value += l; examples += pt->lens[s] - 1;           /* :157-158 (fresh, not stale, value) */
-            if (sync) { /* barrier-coupled optimizer [wyrm-recalled]: steps applied one thread at a time, in order */
+            if (sync) { /* barrier-coupled optimizer [wyrm-recalled]: every thread's gradients come from the round-start
+                           parameters; the sparse entries are applied one thread at a time, in order, un-merged; the
+                           dense parameters take ONE step on the gradient summed over the round (the engine's documented
+                           synchronous semantics) */
                 pthread_barrier_wait(pt->barrier);
-                if (pt->p == 0) for (int q = 0; q < pt->P; ++q) apply_update(m, all[q].ws);
+                if (pt->p == 0) {
+                    float c1, c2;
+                    m->num_updates += (uint64_t)pt->P;
+                    adam_coeffs(m, m->num_updates, &c1, &c2);
+                    float* sum = all[0].ws->dense_grad;
+                    for (int q = 1; q < pt->P; ++q) for (size_t k = 0; k < m->ndense; ++k) sum[k] += all[q].ws->dense_grad[k];
+                    for (int q = 0; q < pt->P; ++q) apply_sparse(m, all[q].ws, c1, c2);
+                    apply_dense(m, sum, c1, c2);
+                }
                 pthread_barrier_wait(pt->barrier);
             } else apply_update(m, pt->ws);                         /* :168 (Hogwild when P > 1) */
         }

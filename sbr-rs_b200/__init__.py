@@ -43,7 +43,7 @@ EXPORTS = [
     "sbr_model_parameter_len", "sbr_model_get_parameter", "sbr_model_set_parameter", "sbr_model_get_num_updates",
     "sbr_model_set_num_updates", "sbr_model_get_rng_state", "sbr_model_set_rng_state", "sbr_model_free",
     "sbr_hyper_shard", "sbr_hyper_virtual_shards", "sbr_model_ipc_handle_size", "sbr_model_ipc_export",
-    "sbr_model_ipc_attach",
+    "sbr_model_ipc_attach", "sbr_dist_unique_id", "sbr_dist_init", "sbr_dist_finalize",
     "sbr_fit_plan_create", "sbr_fit_plan_run", "sbr_fit_plan_stats", "sbr_fit_plan_free", "sbr_model_last_fit_stats",
 ]
 
@@ -144,6 +144,9 @@ def lib():
     L.sbr_model_ipc_handle_size.restype = C.c_size_t
     L.sbr_model_ipc_export.argtypes = [vp, C.c_void_p]
     L.sbr_model_ipc_attach.argtypes = [vp, C.c_void_p]
+    L.sbr_dist_unique_id.argtypes = [u8p]
+    L.sbr_dist_init.argtypes = [C.c_int, C.c_int, u8p]
+    L.sbr_dist_finalize.restype = None
     L.sbr_fit_plan_create.argtypes = [vp, vp, C.POINTER(vp)]
     L.sbr_fit_plan_run.argtypes = [vp, f32p]
     L.sbr_fit_plan_stats.argtypes = [vp, C.POINTER(FitStats)]
@@ -178,6 +181,21 @@ def device_count():
 
 def set_device(i):
     _check(lib().sbr_set_device(i))
+
+
+def dist_unique_id():
+    buf = (C.c_uint8 * 128)()
+    _check(lib().sbr_dist_unique_id(buf))
+    return bytes(buf)
+
+
+def dist_init(rank, world, unique_id):
+    buf = (C.c_uint8 * 128)(*unique_id)
+    _check(lib().sbr_dist_init(rank, world, buf))
+
+
+def dist_finalize():
+    lib().sbr_dist_finalize()
 
 
 # ----------------------------------------------------------------------------------------------- data.rs ----

@@ -22,6 +22,8 @@
 #include <string>
 #include <vector>
 
+#include <nccl.h>
+
 #include "../../include/sbr_b200.h"
 #include "engine.h"
 
@@ -31,6 +33,8 @@ namespace {
 
 thread_local std::string g_err;
 int g_device = 0;
+ncclComm_t g_comm = nullptr;   // process-wide communicator for the synchronous exchange (sbr_dist_init)
+int g_rank = 0, g_world = 1;
 
 sbr_status fail(sbr_status s, const std::string& msg) { g_err = msg; return s; }
 sbr_status cuda_fail(cudaError_t e, const char* what) {
@@ -195,7 +199,9 @@ struct sbr_fit_plan {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     sbr_fit_stats stats{};
     bool scratch_borrowed = false;
+    SyncBuffers* sync = nullptr;
     ~sbr_fit_plan() {
+        if (sync) sync_buffers_free(sync);
         if (d_seq_start) cudaFree(d_seq_start);
         if (d_seq_len) cudaFree(d_seq_len);
         if (dev.order) cudaFree(dev.order);
@@ -498,6 +504,32 @@ sbr_status sbr_hyper_virtual_shards(sbr_hyperparameters* h, int g) {
     return SBR_OK;
 }
 
+sbr_status sbr_dist_unique_id(uint8_t out[128]) {
+    if (!out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    ncclResult_t r = ncclGetUniqueId(&id);
+    if (r != ncclSuccess) return fail(SBR_ERR_NCCL, std::string("ncclGetUniqueId: ") + ncclGetErrorString(r));
+    std::memcpy(out, &id, 128);
+    return SBR_OK;
+}
+sbr_status sbr_dist_init(int rank, int world, const uint8_t id_bytes[128]) {
+    if (!id_bytes || world < 1 || rank < 0 || rank >= world) return fail(SBR_ERR_INVALID_ARGUMENT, "bad rank / world / id");
+    sbr_status s = require_device();
+    if (s) return s;
+    if (g_comm) { ncclCommDestroy(g_comm); g_comm = nullptr; }
+    ncclUniqueId id;
+    std::memcpy(&id, id_bytes, 128);
+    ncclResult_t r = ncclCommInitRank(&g_comm, world, id, rank);
+    if (r != ncclSuccess) { g_comm = nullptr; return fail(SBR_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r)); }
+    g_rank = rank; g_world = world;
+    return SBR_OK;
+}
+void sbr_dist_finalize(void) {
+    if (g_comm) { ncclCommDestroy(g_comm); g_comm = nullptr; }
+    g_rank = 0; g_world = 1;
+}
+
 size_t sbr_model_ipc_handle_size(void) { return 3 * sizeof(cudaIpcMemHandle_t); }
 
 sbr_status sbr_model_ipc_export(const sbr_model* m, void* out) {
@@ -618,7 +650,6 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     sbr_status s = require_device();
     if (s) return s;
     if (c->num_items > m->dev.N) return fail(SBR_ERR_INVALID_ARGUMENT, "interactions.num_items exceeds the model's num_items");
-    if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before using it");
     const double t0 = now_ms();
     const size_t T = (size_t)m->dev.T;
     // the id stream goes to HBM (narrowed to u32, pinned double buffer) while the host builds the schedule
@@ -744,7 +775,20 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
     CU(cudaMemsetAsync(pl->dev.examples, 0, P * sizeof(unsigned long long), st));
     int launches = 0;
     CU(cudaEventRecord(pl->evk0, st));
-    if (pl->dev.epochs > 0) {
+    const char* why = nullptr;
+    const bool sync_mode = m->h.parallelism == SBR_PARALLELISM_SYNCHRONOUS && (P > 1 || g_world > 1) && sync_supported(m->dev, &why) &&
+                           (int)(m->dev.gmask + 1) == (m->h.shard_world > 1 ? m->h.shard_world : 1);
+    if (pl->dev.epochs > 0 && sync_mode) {
+        // Parallelism::Synchronous: round-synchronous schedule with an explicit row exchange (sync_engine.cu)
+        const int world = m->h.shard_world > 1 ? m->h.shard_world : 1;
+        if (world > 1 && (!g_comm || g_world != world || g_rank != m->h.shard_rank))
+            return fail(SBR_ERR_NCCL, "synchronous multi-GPU fit needs sbr_dist_init(rank, world, id) matching sbr_hyper_shard");
+        if (!pl->sync) pl->sync = sync_buffers_new();
+        std::string err;
+        const int rc = run_sync_ewma(m->dev, pl->dev, *pl->sync, g_comm, m->h.shard_rank, world, m->num_updates, st, &launches, &err);
+        if (rc) return fail(rc == 2 ? SBR_ERR_NCCL : rc == 3 ? SBR_ERR_INVALID_ARGUMENT : SBR_ERR_CUDA, err);
+    } else if (pl->dev.epochs > 0) {
+        if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before an asynchronous fit");
         cudaError_t e;
         launches = launch_train(m->dev, pl->dev, device_info().sms, st, &e);
         if (e != cudaSuccess) return cuda_fail(e, "launch_train");

@@ -66,6 +66,17 @@ bool train_supported(const ModelDev& m, const char** why);
 int lstm_kernel_choice(const ModelDev& m, uint32_t P);
 cudaError_t launch_lstm_tc(const ModelDev& m, const PlanDev& p, int nt, cudaStream_t st);
 
+// round-synchronous engine (sync_engine.cu)
+struct SyncBuffers;
+SyncBuffers* sync_buffers_new();
+void sync_buffers_free(SyncBuffers* b);
+bool sync_supported(const ModelDev& m, const char** why);
+}  // namespace sbr
+#include <string>
+namespace sbr {
+int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm, int rank, int world, uint64_t num_updates,
+                  cudaStream_t st, int* launches, std::string* err);
+
 cudaError_t launch_gather_rows(const ModelDev& m, const uint32_t* ids_dev, size_t n, float* out_dev, cudaStream_t st);
 cudaError_t launch_user_representations(const ModelDev& m, const uint64_t* ptr_dev, const uint32_t* ids_dev, size_t num_users,
                                         float* out_dev, cudaStream_t st);
