@@ -776,6 +776,7 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
     int launches = 0;
     CU(cudaEventRecord(pl->evk0, st));
     const char* why = nullptr;
+    uint64_t sync_rounds = 0;
     const bool sync_mode = m->h.parallelism == SBR_PARALLELISM_SYNCHRONOUS && (P > 1 || g_world > 1) && sync_supported(m->dev, &why) &&
                            (int)(m->dev.gmask + 1) == (m->h.shard_world > 1 ? m->h.shard_world : 1);
     if (pl->dev.epochs > 0 && sync_mode) {
@@ -785,7 +786,7 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
             return fail(SBR_ERR_NCCL, "synchronous multi-GPU fit needs sbr_dist_init(rank, world, id) matching sbr_hyper_shard");
         if (!pl->sync) pl->sync = sync_buffers_new();
         std::string err;
-        const int rc = run_sync_ewma(m->dev, pl->dev, *pl->sync, g_comm, m->h.shard_rank, world, m->num_updates, st, &launches, &err);
+        const int rc = run_sync_ewma(m->dev, pl->dev, *pl->sync, g_comm, m->h.shard_rank, world, m->num_updates, st, &launches, &sync_rounds, &err);
         if (rc) return fail(rc == 2 ? SBR_ERR_NCCL : rc == 3 ? SBR_ERR_INVALID_ARGUMENT : SBR_ERR_CUDA, err);
     } else if (pl->dev.epochs > 0) {
         if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before an asynchronous fit");
@@ -801,7 +802,7 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
     CU(cudaStreamSynchronize(st));
     float total = 0.0f; uint64_t tsteps = 0;
     for (size_t p = 0; p < P; ++p) { total += loss[p] / (1.0f + (float)ex[p]); tsteps += ex[p]; }  // :173-175
-    const uint64_t steps = (uint64_t)P * pl->n * (uint64_t)pl->dev.epochs;
+    const uint64_t steps = (sync_mode && pl->dev.epochs > 0) ? (uint64_t)P * sync_rounds : (uint64_t)P * pl->n * (uint64_t)pl->dev.epochs;
     m->num_updates += steps;
     float kms = 0.0f, tms = 0.0f;
     CU(cudaEventElapsedTime(&kms, pl->evk0, pl->evk1));

@@ -75,7 +75,7 @@ bool sync_supported(const ModelDev& m, const char** why);
 #include <string>
 namespace sbr {
 int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm, int rank, int world, uint64_t num_updates,
-                  cudaStream_t st, int* launches, std::string* err);
+                  cudaStream_t st, int* launches, uint64_t* rounds_out, std::string* err);
 
 cudaError_t launch_gather_rows(const ModelDev& m, const uint32_t* ids_dev, size_t n, float* out_dev, cudaStream_t st);
 cudaError_t launch_user_representations(const ModelDev& m, const uint64_t* ptr_dev, const uint32_t* ids_dev, size_t num_users,

@@ -289,7 +289,7 @@ size_t sync_scratch_floats_per_partition(const ModelDev& m) { return (((size_t)m
 
 // returns 0 ok, 1 cuda error, 2 nccl error, 3 capacity error.  `comm` may be null when world == 1.
 int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, int rank, int world, uint64_t num_updates,
-                  cudaStream_t st, int* launches, std::string* err) {
+                  cudaStream_t st, int* launches, uint64_t* rounds_out, std::string* err) {
     ncclComm_t comm = static_cast<ncclComm_t>(comm_v);
     const int G = world, D = m.D, Tm1 = m.T - 1;
     const size_t nslots = (size_t)pl.P * Tm1 * 3;
@@ -332,10 +332,21 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
         return ncclGroupEnd();
     };
 
+    // every rank must run the same number of rounds (collectives inside): the ranks agree on the smallest partition length
+    uint32_t n_rounds = pl.n;
+    if (world > 1) {
+        B.h_counts[64] = pl.n;
+        SCU(cudaMemcpyAsync(counts, &B.h_counts[64], 4, cudaMemcpyHostToDevice, st));
+        SNC(ncclAllReduce(counts, counts, 1, ncclUint32, ncclMin, comm, st));
+        SCU(cudaMemcpyAsync(&B.h_counts[64], counts, 4, cudaMemcpyDeviceToHost, st));
+        SCU(cudaStreamSynchronize(st));
+        n_rounds = B.h_counts[64];
+    }
+    *rounds_out = (uint64_t)n_rounds * (uint64_t)pl.epochs;
     for (int ep = 0; ep < pl.epochs; ++ep) {
         sync_shuffle_kernel<<<(pl.P + 127) / 128, 128, 0, st>>>(pl);
         ++*launches;
-        for (uint32_t it = 0; it < pl.n; ++it, ++rounds_done) {
+        for (uint32_t it = 0; it < n_rounds; ++it, ++rounds_done) {
             // 1. requests + bucketing by owner
             SCU(cudaMemsetAsync(counts, 0, 64, st));
             sync_request_kernel<<<148 * 8, 256, 0, st>>>(m, pl, it, 0, (uint32_t)rank * pl.P, req_id, req_ord);

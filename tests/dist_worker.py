@@ -66,7 +66,8 @@ def main():
         H = pkg.lstm.Hyperparameters if kind == "lstm" else pkg.ewma.Hyperparameters
         def hyper():
             h = H(N, T).embedding_dim(D).learning_rate(0.05).l2_penalty(1e-4).loss(pkg.Loss.BPR) \
-                .optimizer(pkg.Optimizer.Adagrad).num_epochs(1).num_threads(8).from_seed(seed)
+                .optimizer(pkg.Optimizer.Adagrad).parallelism(pkg.Parallelism.Asynchronous).num_epochs(1).num_threads(8) \
+                .from_seed(seed)
             return h.lstm_variant(pkg.LSTMVariant.Normal) if kind == "lstm" else h
         ref = hyper().build()                                   # unsharded twin, local
         model = hyper().shard(rank, world).build()
@@ -102,6 +103,43 @@ def main():
             print("dist_worker %s OK world=%d losses=%s" % (kind, world, [round(x, 4) for x in losses]))
         dist.barrier()
         del model, ref
+    # ---- Parallelism::Synchronous across GPUs: NCCL all-to-all exchange of ids / rows / gradient rows (sync_engine.cu) ----
+    uid = [pkg.dist_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    pkg.dist_init(rank, world, uid[0])
+    Nbig = 300_001
+    ids_big = np.random.default_rng(3).integers(1, Nbig, size=int(ptr[-1])).astype(np.uint64)
+    my_ptr2, my_ids2 = split_users(ptr, ids_big, rank, world)
+    hs = (pkg.ewma.Hyperparameters(Nbig, T).embedding_dim(D).learning_rate(0.05).l2_penalty(1e-4).loss(pkg.Loss.BPR)
+          .optimizer(pkg.Optimizer.Adagrad).parallelism(pkg.Parallelism.Synchronous).num_epochs(1).num_threads(8)
+          .from_seed(seed).shard(rank, world))
+    sm = hs.build()
+    sm.ipc_attach(exchange_handles(sm, world))   # only so that get_parameter can read every shard; fit() does not use it
+    e0 = sm.get_parameter("item_embeddings").copy()
+    data2 = pkg.CompressedInteractions.from_csr(my_ptr2, my_ids2, None, num_items=Nbig)
+    sl = []
+    for _ in range(4):
+        dist.barrier()
+        sl.append(sm.fit(data2) / 8)
+    dist.barrier()
+    e1 = sm.get_parameter("item_embeddings")
+    al = torch.tensor(sm.get_parameter("alpha").astype(np.float64))
+    als = [torch.zeros_like(al) for _ in range(world)]
+    dist.all_gather(als, al)
+    for t in als:
+        assert torch.equal(t, als[0])                            # dense replicas stay bit-identical
+    assert np.all(np.isfinite(e1)) and np.abs(e1 - e0).max() > 1e-3 and sl[-1] < sl[0], sl
+    chk = torch.tensor([float(np.abs(e1).sum())], dtype=torch.float64)
+    chks = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(chks, chk)
+    assert all(torch.equal(c, chks[0]) for c in chks)           # every rank reads the same table
+    st = sm.last_fit_stats()
+    assert st["kernel_launches"] > 10
+    if rank == 0:
+        print("dist_worker sync OK world=%d losses=%s launches=%d" % (world, [round(x, 4) for x in sl], st["kernel_launches"]))
+    dist.barrier()
+    del sm
+    pkg.dist_finalize()
     dist.destroy_process_group()
 
 

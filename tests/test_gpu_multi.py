@@ -17,6 +17,7 @@ def test_two_gpu_shared_model(pkg):
     world = 2 if n < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr",
            "127.0.0.1", "--master-port", "29612", os.path.join(ROOT, "tests", "dist_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "dist_worker ewma OK" in out.stdout and "dist_worker lstm OK" in out.stdout
+    assert "dist_worker sync OK" in out.stdout
