@@ -170,14 +170,27 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
     // instruction): [T][8 arrays][8 chunks of 4 d][128 seq] float4, then G, NEG [T][128]
     float* sbase = pl.scratch + (size_t)tile_gid * 128 * pl.scratch_stride;
     float* G_ = sbase + (size_t)T * 8 * 32 * 128; uint32_t* NEG = reinterpret_cast<uint32_t*>(G_ + (size_t)T * 128);
-    auto sc4 = [&](int t, int which, int c4) -> float4* {
-        return reinterpret_cast<float4*>(sbase) + (((size_t)t * 8 + which) * 8 + c4) * 128 + r;
+    // per timestep: fp32 arrays C, H ([2][8 chunks][128] float4) then bf16 arrays F, I, G, O, X, DQ ([6][4 chunks][128] uint4):
+    // 80 KB per tile-timestep.  The backward products are bf16 anyway (delta tile, Z tile), so gates / x / dq are kept in
+    // bf16; the cell and hidden states stay fp32.
+    constexpr int kStepU4 = (16 + 24) * 128;   // uint4 units per timestep
+    auto sf4 = [&](int t, int which /*0 C, 1 H*/, int c4) -> float4* {
+        return reinterpret_cast<float4*>(sbase) + (size_t)t * kStepU4 + (size_t)(which * 8 + c4) * 128 + r;
     };
-    // pull one timestep of the tile's scratch (128 KB = 1024 lines) towards L2: 8 lines per thread
+    auto sb8 = [&](int t, int which /*0 F,1 I,2 G,3 O,4 X,5 DQ*/, int c8) -> uint4* {
+        return reinterpret_cast<uint4*>(sbase) + (size_t)t * kStepU4 + (size_t)(16 + which * 4 + c8) * 128 + r;
+    };
+    // pull one timestep of the tile's scratch (80 KB = 640 lines) towards L2: 5 lines per thread
     auto prefetch_step = [&](int t) {
-        const char* base = reinterpret_cast<const char*>(sbase) + (size_t)t * 8 * 32 * 128 * 4 + (size_t)r * 8 * 128;
+        const char* base = reinterpret_cast<const char*>(sbase) + (size_t)t * kStepU4 * 16 + (size_t)r * 5 * 128;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i * 128));
+        for (int i = 0; i < 5; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i * 128));
+    };
+    auto unpack8 = [](const uint4& u, float (&v)[8]) {
+        v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+        v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+        v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xffff0000u);
+        v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
     };
 
     // ---- one-time setup ----
@@ -266,7 +279,10 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                     }
                     if (act) {
 #pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) *sc4(t, SX, c4) = make_float4(x[4 * c4], x[4 * c4 + 1], x[4 * c4 + 2], x[4 * c4 + 3]);
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            const float x8[8] = {x[8 * c8], x[8 * c8 + 1], x[8 * c8 + 2], x[8 * c8 + 3], x[8 * c8 + 4], x[8 * c8 + 5], x[8 * c8 + 6], x[8 * c8 + 7]};
+                            *sb8(t, 4, c8) = pack_bf16x8(x8);
+                        }
                     }
                 }
                 fence_async_smem();
@@ -304,15 +320,13 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                         pf[j] = f; pi[j] = ig; pg[j] = gg; po[j] = og;
                     }
                     if (act) {
+                        *sb8(t, 0, db) = pack_bf16x8(pf); *sb8(t, 1, db) = pack_bf16x8(pi);
+                        *sb8(t, 2, db) = pack_bf16x8(pg); *sb8(t, 3, db) = pack_bf16x8(po);
 #pragma unroll
                         for (int hf = 0; hf < 2; ++hf) {
-                            const int c4 = db * 2 + hf, q = hf * 4;
-                            *sc4(t, SF, c4) = make_float4(pf[q], pf[q + 1], pf[q + 2], pf[q + 3]);
-                            *sc4(t, SI, c4) = make_float4(pi[q], pi[q + 1], pi[q + 2], pi[q + 3]);
-                            *sc4(t, SG, c4) = make_float4(pg[q], pg[q + 1], pg[q + 2], pg[q + 3]);
-                            *sc4(t, SO, c4) = make_float4(po[q], po[q + 1], po[q + 2], po[q + 3]);
-                            *sc4(t, SC, c4) = make_float4(c[4 * c4], c[4 * c4 + 1], c[4 * c4 + 2], c[4 * c4 + 3]);
-                            *sc4(t, SH, c4) = make_float4(h[4 * c4], h[4 * c4 + 1], h[4 * c4 + 2], h[4 * c4 + 3]);
+                            const int c4 = db * 2 + hf;
+                            *sf4(t, 0, c4) = make_float4(c[4 * c4], c[4 * c4 + 1], c[4 * c4 + 2], c[4 * c4 + 3]);
+                            *sf4(t, 1, c4) = make_float4(h[4 * c4], h[4 * c4 + 1], h[4 * c4 + 2], h[4 * c4 + 3]);
                         }
                     }
                 }
@@ -346,9 +360,12 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                     else { const float v = 1.0f + ngs - pos; l = v > 0.0f ? v : 0.0f; g = v > 0.0f ? 1.0f : 0.0f; }
                     loss_seq += l;
 #pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4)
-                        *sc4(t, SDQ, c4) = make_float4(g * (qv[4 * c4] - pv[4 * c4]), g * (qv[4 * c4 + 1] - pv[4 * c4 + 1]),
-                                                       g * (qv[4 * c4 + 2] - pv[4 * c4 + 2]), g * (qv[4 * c4 + 3] - pv[4 * c4 + 3]));
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        float d8[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) d8[e] = g * (qv[8 * c8 + e] - pv[8 * c8 + e]);
+                        *sb8(t, 5, c8) = pack_bf16x8(d8);
+                    }
                     G_[(size_t)t * 128 + r] = g; NEG[(size_t)t * 128 + r] = neg;
                 }
             }
@@ -367,47 +384,49 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc_train_kernel(ModelDev m, 
                 if (act) { g = G_[(size_t)t * 128 + r]; neg = NEG[(size_t)t * 128 + r]; in = __ldg(ids + t); out = __ldg(ids + t + 1); }
 #pragma unroll
                 for (int db = 0; db < 4; ++db) {
-                    float df[8], di[8], dg[8], dO[8], hp8[8], x8[8];
+                    float df[8], di[8], dg[8], dO[8], hp8[8];
+                    float f8[8], i8[8], g8[8], o8[8], q8[8], c8v[8], cp8[8], h8[8];
+                    uint4 xraw = make_uint4(0u, 0u, 0u, 0u);
+                    if (act) {
+                        const uint4 uf = *sb8(t, 0, db), ui = *sb8(t, 1, db), ug = *sb8(t, 2, db), uo = *sb8(t, 3, db), uq = *sb8(t, 5, db);
+                        xraw = *sb8(t, 4, db);
+                        const float4 ca = *sf4(t, 0, 2 * db), cb = *sf4(t, 0, 2 * db + 1), ha = *sf4(t, 1, 2 * db), hb = *sf4(t, 1, 2 * db + 1);
+                        float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa, hpa = pa, hpb = pa;
+                        if (t > 0) { pa = *sf4(t - 1, 0, 2 * db); pb = *sf4(t - 1, 0, 2 * db + 1); hpa = *sf4(t - 1, 1, 2 * db); hpb = *sf4(t - 1, 1, 2 * db + 1); }
+                        unpack8(uf, f8); unpack8(ui, i8); unpack8(ug, g8); unpack8(uo, o8); unpack8(uq, q8);
+                        c8v[0] = ca.x; c8v[1] = ca.y; c8v[2] = ca.z; c8v[3] = ca.w; c8v[4] = cb.x; c8v[5] = cb.y; c8v[6] = cb.z; c8v[7] = cb.w;
+                        cp8[0] = pa.x; cp8[1] = pa.y; cp8[2] = pa.z; cp8[3] = pa.w; cp8[4] = pb.x; cp8[5] = pb.y; cp8[6] = pb.z; cp8[7] = pb.w;
+                        h8[0] = ha.x; h8[1] = ha.y; h8[2] = ha.z; h8[3] = ha.w; h8[4] = hb.x; h8[5] = hb.y; h8[6] = hb.z; h8[7] = hb.w;
+                        hp8[0] = hpa.x; hp8[1] = hpa.y; hp8[2] = hpa.z; hp8[3] = hpa.w; hp8[4] = hpb.x; hp8[5] = hpb.y; hp8[6] = hpb.z; hp8[7] = hpb.w;
+                    } else {
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const int c4 = db * 2 + hf;
-                        float4 f4, i4, g4, o4, ct4, dq4, cp4, h4, hp4, x4;
-                        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (act) {
-                            f4 = *sc4(t, SF, c4); i4 = *sc4(t, SI, c4); g4 = *sc4(t, SG, c4); o4 = *sc4(t, SO, c4);
-                            ct4 = *sc4(t, SC, c4); dq4 = *sc4(t, SDQ, c4); h4 = *sc4(t, SH, c4); x4 = *sc4(t, SX, c4);
-                            cp4 = t > 0 ? *sc4(t - 1, SC, c4) : z4; hp4 = t > 0 ? *sc4(t - 1, SH, c4) : z4;
-                        } else { f4 = i4 = g4 = o4 = ct4 = dq4 = cp4 = h4 = hp4 = x4 = z4; }
-                        // gradient of the two rows that only need h_t goes straight to the staging slice
-                        *reinterpret_cast<float4*>(stage_b + lane * kSS + c4 * 4) = make_float4(g * h4.x, g * h4.y, g * h4.z, g * h4.w);
-                        const float fa[4] = {f4.x, f4.y, f4.z, f4.w}, ia[4] = {i4.x, i4.y, i4.z, i4.w}, ga[4] = {g4.x, g4.y, g4.z, g4.w};
-                        const float oa[4] = {o4.x, o4.y, o4.z, o4.w}, ca[4] = {ct4.x, ct4.y, ct4.z, ct4.w}, qa[4] = {dq4.x, dq4.y, dq4.z, dq4.w};
-                        const float pa[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
-                        hp8[hf * 4] = hp4.x; hp8[hf * 4 + 1] = hp4.y; hp8[hf * 4 + 2] = hp4.z; hp8[hf * 4 + 3] = hp4.w;
-                        x8[hf * 4] = x4.x; x8[hf * 4 + 1] = x4.y; x8[hf * 4 + 2] = x4.z; x8[hf * 4 + 3] = x4.w;
+                        for (int e = 0; e < 8; ++e) { f8[e] = i8[e] = g8[e] = o8[e] = q8[e] = c8v[e] = cp8[e] = h8[e] = hp8[e] = 0.0f; }
+                    }
+                    // gradient of the two rows that only need h_t goes straight to the staging slice
+                    *reinterpret_cast<float4*>(stage_b + lane * kSS + (2 * db) * 4) = make_float4(g * h8[0], g * h8[1], g * h8[2], g * h8[3]);
+                    *reinterpret_cast<float4*>(stage_b + lane * kSS + (2 * db + 1) * 4) = make_float4(g * h8[4], g * h8[5], g * h8[6], g * h8[7]);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int d = c4 * 4 + e, j = hf * 4 + e;
-                            const float tcv = fast_tanh(ca[e]);
-                            const float dh = dh_rec[d] + qa[e];
-                            const float d_o = dh * tcv;
-                            const float dc = dc_rec[d] + dh * oa[e] * (1.0f - tcv * tcv);
-                            float d_f = dc * pa[e], d_i = dc * ga[e];
-                            const float d_g = dc * ia[e];
-                            dc_rec[d] = act ? dc * fa[e] : 0.0f;
-                            if (coupled) { d_f -= d_i; d_i = 0.0f; }
-                            df[j] = d_f * fa[e] * (1.0f - fa[e]);
-                            di[j] = coupled ? 0.0f : d_i * ia[e] * (1.0f - ia[e]);
-                            dg[j] = d_g * (1.0f - ga[e] * ga[e]);
-                            dO[j] = d_o * oa[e] * (1.0f - oa[e]);
-                        }
+                    for (int e = 0; e < 8; ++e) {
+                        const int d = db * 8 + e;
+                        const float tcv = fast_tanh(c8v[e]);
+                        const float dh = dh_rec[d] + q8[e];
+                        const float d_o = dh * tcv;
+                        const float dc = dc_rec[d] + dh * o8[e] * (1.0f - tcv * tcv);
+                        float d_f = dc * cp8[e], d_i = dc * g8[e];
+                        const float d_g = dc * i8[e];
+                        dc_rec[d] = act ? dc * f8[e] : 0.0f;
+                        if (coupled) { d_f -= d_i; d_i = 0.0f; }
+                        df[e] = d_f * f8[e] * (1.0f - f8[e]);
+                        di[e] = coupled ? 0.0f : d_i * i8[e] * (1.0f - i8[e]);
+                        dg[e] = d_g * (1.0f - g8[e] * g8[e]);
+                        dO[e] = d_o * o8[e] * (1.0f - o8[e]);
                     }
                     *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 0 + db, 16)) = pack_bf16x8(df);
                     *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 4 + db, 16)) = pack_bf16x8(di);
                     *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 8 + db, 16)) = pack_bf16x8(dg);
                     *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 12 + db, 16)) = pack_bf16x8(dO);
                     *reinterpret_cast<uint4*>(Zb + tile_chunk_off(r, db, 10)) = pack_bf16x8(hp8);      // Z_t = [h_{t-1}, x_t]
-                    *reinterpret_cast<uint4*>(Zb + tile_chunk_off(r, 4 + db, 10)) = pack_bf16x8(x8);
+                    *reinterpret_cast<uint4*>(Zb + tile_chunk_off(r, 4 + db, 10)) = xraw;               // x_t was saved as bf16
                 }
                 fence_async_smem();
                 tc_fence_before_sync();
