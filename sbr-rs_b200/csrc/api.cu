@@ -22,12 +22,45 @@
 #include <string>
 #include <vector>
 
-#include <nccl.h>
+#include <dlfcn.h>
+#include <type_traits>
 
 #include "../../include/sbr_b200.h"
 #include "engine.h"
+#include "nccl_dyn.h"
 
 using namespace sbr;
+
+namespace sbr {
+// NCCL is resolved on first use (nccl_dyn.h): the copy already mapped in the process, else the system library.
+const NcclApi* nccl_api(std::string* why) {
+    static NcclApi api;
+    static std::string err;
+    static std::once_flag once;
+    static bool ok = false;
+    std::call_once(once, []() {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (!h) { const char* e = dlerror(); err = std::string("cannot load libnccl.so.2: ") + (e ? e : "?"); return; }
+        bool all = true;
+        auto bind = [&](auto& fn, const char* name) {
+            void* s = dlsym(h, name);
+            if (!s) { all = false; err = std::string("libnccl.so.2 lacks ") + name; }
+            fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(s);
+        };
+        bind(api.GetUniqueId, "ncclGetUniqueId"); bind(api.CommInitRank, "ncclCommInitRank");
+        bind(api.CommDestroy, "ncclCommDestroy"); bind(api.GetErrorString, "ncclGetErrorString");
+        bind(api.GroupStart, "ncclGroupStart"); bind(api.GroupEnd, "ncclGroupEnd");
+        bind(api.Send, "ncclSend"); bind(api.Recv, "ncclRecv");
+        bind(api.AllReduce, "ncclAllReduce"); bind(api.AllGather, "ncclAllGather");
+        bind(api.GetVersion, "ncclGetVersion");
+        ok = all;
+    });
+    if (!ok) { if (why) *why = err; return nullptr; }
+    return &api;
+}
+}  // namespace sbr
 
 namespace {
 
@@ -507,9 +540,12 @@ sbr_status sbr_hyper_virtual_shards(sbr_hyperparameters* h, int g) {
 sbr_status sbr_dist_unique_id(uint8_t out[128]) {
     if (!out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::string why;
+    const NcclApi* nc = nccl_api(&why);
+    if (!nc) return fail(SBR_ERR_NCCL, why);
     ncclUniqueId id;
-    ncclResult_t r = ncclGetUniqueId(&id);
-    if (r != ncclSuccess) return fail(SBR_ERR_NCCL, std::string("ncclGetUniqueId: ") + ncclGetErrorString(r));
+    ncclResult_t r = nc->GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(SBR_ERR_NCCL, std::string("ncclGetUniqueId: ") + nc->GetErrorString(r));
     std::memcpy(out, &id, 128);
     return SBR_OK;
 }
@@ -517,16 +553,19 @@ sbr_status sbr_dist_init(int rank, int world, const uint8_t id_bytes[128]) {
     if (!id_bytes || world < 1 || rank < 0 || rank >= world) return fail(SBR_ERR_INVALID_ARGUMENT, "bad rank / world / id");
     sbr_status s = require_device();
     if (s) return s;
-    if (g_comm) { ncclCommDestroy(g_comm); g_comm = nullptr; }
+    std::string why;
+    const NcclApi* nc = nccl_api(&why);
+    if (!nc) return fail(SBR_ERR_NCCL, why);
+    if (g_comm) { nc->CommDestroy(g_comm); g_comm = nullptr; }
     ncclUniqueId id;
     std::memcpy(&id, id_bytes, 128);
-    ncclResult_t r = ncclCommInitRank(&g_comm, world, id, rank);
-    if (r != ncclSuccess) { g_comm = nullptr; return fail(SBR_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r)); }
+    ncclResult_t r = nc->CommInitRank(&g_comm, world, id, rank);
+    if (r != ncclSuccess) { g_comm = nullptr; return fail(SBR_ERR_NCCL, std::string("ncclCommInitRank: ") + nc->GetErrorString(r)); }
     g_rank = rank; g_world = world;
     return SBR_OK;
 }
 void sbr_dist_finalize(void) {
-    if (g_comm) { ncclCommDestroy(g_comm); g_comm = nullptr; }
+    if (g_comm) { if (const NcclApi* nc = nccl_api(nullptr)) nc->CommDestroy(g_comm); g_comm = nullptr; }
     g_rank = 0; g_world = 1;
 }
 

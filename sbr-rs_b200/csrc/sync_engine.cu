@@ -14,7 +14,6 @@
 // items/2 GPUs 2.4M steps/s, 50M items/8 GPUs 0.65M steps/s -- fabric-side address translation thrashes).
 // With one GPU the same kernels run without NCCL (the exchange is the identity).
 #include <cuda_runtime.h>
-#include <nccl.h>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -23,6 +22,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "nccl_dyn.h"
 
 namespace sbr {
 
@@ -277,7 +277,7 @@ SyncBuffers* sync_buffers_new() { return new SyncBuffers(); }
 void sync_buffers_free(SyncBuffers* b) { delete b; }
 
 #define SCU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { *err = std::string(#expr) + ": " + cudaGetErrorString(e__); return 1; } } while (0)
-#define SNC(expr) do { ncclResult_t r__ = (expr); if (r__ != ncclSuccess) { *err = std::string(#expr) + ": " + ncclGetErrorString(r__); return 2; } } while (0)
+#define SNC(expr) do { ncclResult_t r__ = (expr); if (r__ != ncclSuccess) { *err = std::string(#expr) + ": " + NC->GetErrorString(r__); return 2; } } while (0)
 
 bool sync_supported(const ModelDev& m, const char** why) {
     if (m.model != MODEL_EWMA) { *why = "Parallelism::Synchronous with num_threads > 1 is implemented for the EWMA model only"; return false; }
@@ -291,6 +291,8 @@ size_t sync_scratch_floats_per_partition(const ModelDev& m) { return (((size_t)m
 int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, int rank, int world, uint64_t num_updates,
                   cudaStream_t st, int* launches, uint64_t* rounds_out, std::string* err) {
     ncclComm_t comm = static_cast<ncclComm_t>(comm_v);
+    const NcclApi* NC = nullptr;
+    if (world > 1) { NC = nccl_api(err); if (!NC) return 2; }
     const int G = world, D = m.D, Tm1 = m.T - 1;
     const size_t nslots = (size_t)pl.P * Tm1 * 3;
     const size_t cap_own = world == 1 ? nslots : nslots * 3 / 2 + 4096;  // rows other ranks may request from this shard per round
@@ -323,13 +325,13 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
 
     auto exchange = [&](const void* sendbuf, const size_t* scnt, const size_t* soff, void* recvbuf, const size_t* rcnt, const size_t* roff,
                         size_t elem) -> ncclResult_t {
-        ncclResult_t r = ncclGroupStart();
+        ncclResult_t r = NC->GroupStart();
         if (r != ncclSuccess) return r;
         for (int g = 0; g < G; ++g) {
-            if (scnt[g]) { r = ncclSend(static_cast<const char*>(sendbuf) + soff[g] * elem, scnt[g] * elem, ncclChar, g, comm, st); if (r != ncclSuccess) return r; }
-            if (rcnt[g]) { r = ncclRecv(static_cast<char*>(recvbuf) + roff[g] * elem, rcnt[g] * elem, ncclChar, g, comm, st); if (r != ncclSuccess) return r; }
+            if (scnt[g]) { r = NC->Send(static_cast<const char*>(sendbuf) + soff[g] * elem, scnt[g] * elem, ncclChar, g, comm, st); if (r != ncclSuccess) return r; }
+            if (rcnt[g]) { r = NC->Recv(static_cast<char*>(recvbuf) + roff[g] * elem, rcnt[g] * elem, ncclChar, g, comm, st); if (r != ncclSuccess) return r; }
         }
-        return ncclGroupEnd();
+        return NC->GroupEnd();
     };
 
     // every rank must run the same number of rounds (collectives inside): the ranks agree on the smallest partition length
@@ -337,7 +339,7 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
     if (world > 1) {
         B.h_counts[64] = pl.n;
         SCU(cudaMemcpyAsync(counts, &B.h_counts[64], 4, cudaMemcpyHostToDevice, st));
-        SNC(ncclAllReduce(counts, counts, 1, ncclUint32, ncclMin, comm, st));
+        SNC(NC->AllReduce(counts, counts, 1, ncclUint32, ncclMin, comm, st));
         SCU(cudaMemcpyAsync(&B.h_counts[64], counts, 4, cudaMemcpyDeviceToHost, st));
         SCU(cudaStreamSynchronize(st));
         n_rounds = B.h_counts[64];
@@ -356,7 +358,7 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
             size_t scnt[8] = {0}, soff[8] = {0}, rcnt[8] = {0}, roff[8] = {0}, nown = 0;
             const uint32_t* own_rows = send_row; const uint32_t* own_ords = send_ord; const float* rows_for_compute = nullptr; const float* bias_for_compute = nullptr;
             if (world > 1) {
-                SNC(ncclAllGather(counts, B.allcounts.p, 8, ncclUint32, comm, st));
+                SNC(NC->AllGather(counts, B.allcounts.p, 8, ncclUint32, comm, st));
                 SCU(cudaMemcpyAsync(B.h_counts, B.allcounts.p, (size_t)G * 8 * 4, cudaMemcpyDeviceToHost, st));
                 SCU(cudaStreamSynchronize(st));
                 size_t so = 0, ro = 0;
@@ -408,7 +410,7 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
                 *launches += 3;
             }
             // 6. dense parameters: gradient summed over every partition of every rank, one step on each replica
-            if (world > 1) SNC(ncclAllReduce(B.dalpha.p, B.dalpha.p, m.ndense, ncclFloat, ncclSum, comm, st));
+            if (world > 1) SNC(NC->AllReduce(B.dalpha.p, B.dalpha.p, m.ndense, ncclFloat, ncclSum, comm, st));
             sync_dense_kernel<<<(unsigned)((m.ndense + 127) / 128), 128, 0, st>>>(m, static_cast<float*>(B.dalpha.p), o);
             ++*launches;
         }
