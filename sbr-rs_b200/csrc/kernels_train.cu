@@ -763,7 +763,12 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
             default: *err = cudaErrorInvalidValue; return 0;
         }
     } else if (int nt = lstm_kernel_choice(m, p.P)) {
-        *err = launch_lstm_tc(m, p, nt, st);
+        // SBR_LSTM_TC selects the tile-kernel generation: "1" = kernels_lstm_tc.cu, "2" = kernels_lstm_tc2.cu
+        // (prefetching pipeline, exp-based gates), "2f" = the same with MUFU.TANH gates
+        const char* gen = getenv("SBR_LSTM_TC");
+        if (gen && !strcmp(gen, "2")) *err = launch_lstm_tc2(m, p, nt, false, st);
+        else if (gen && !strcmp(gen, "2f")) *err = launch_lstm_tc2(m, p, nt, true, st);
+        else *err = launch_lstm_tc(m, p, nt, st);
         return 1;
     } else {
         dim3 block(kLstmWPC * 32), grid((p.P + kLstmWPC - 1) / kLstmWPC);
