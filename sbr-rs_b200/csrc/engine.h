@@ -66,6 +66,7 @@ bool train_supported(const ModelDev& m, const char** why);
 int lstm_kernel_choice(const ModelDev& m, uint32_t P);
 cudaError_t launch_lstm_tc(const ModelDev& m, const PlanDev& p, int nt, cudaStream_t st);
 cudaError_t launch_lstm_tc2(const ModelDev& m, const PlanDev& p, int nt, bool fast_math, cudaStream_t st);
+cudaError_t launch_lstm_tc3(const ModelDev& m, const PlanDev& p, int nt, int ds, cudaStream_t st);
 
 // round-synchronous engine (sync_engine.cu)
 struct SyncBuffers;

@@ -79,6 +79,26 @@ __device__ __forceinline__ void apply4(float4& w, float4& s, float4& v, const fl
     }
 }
 
+// L2 atomics for the Hogwild Adagrad visits.  A visit as load -> compute -> store makes every hot row a read-modify-write
+// hazard between thousands of concurrent sequences (1,683 rows, 37,888 partitions): measured on the ML-100K-shaped
+// stream the stores alone cost 7 ms and the 16-byte bias records 11 ms of a 44 ms epoch (ablation in DESIGN.md 3.4).
+// The accumulator G is additive, so the visit becomes: {atom.add G += sum g^2 (returns the old G), ld w} in one round
+// trip, the sequential Adagrad applications in registers from the returned G, then two fire-and-forget reductions
+// (w += sum of steps; G += the l2 cross terms).  No update of G is ever lost, and the L2 atomic unit serialises hot
+// addresses at about a cycle per operation instead of a memory round trip.
+__device__ __forceinline__ float4 atom_add4(float* p, const float4& v) {
+    float4 o;
+    asm volatile("atom.global.add.v4.f32 {%0, %1, %2, %3}, [%4], {%5, %6, %7, %8};"
+                 : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    return o;
+}
+__device__ __forceinline__ void red_add4(float* p, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 sq4(const float4& a) { return make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w); }
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 sub4(const float4& a, const float4& b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+
 // ---------------------------------------------------------------------------------------------------------
 // Staging slices.  A slice holds 32 rows x 128 B in core-matrix order: row r, 16-byte chunk c at
 //   (r >> 3) * gs + c * 128 + (r & 7) * 16          (gs = 1024 compact; 1280 inside the bf16 Z tile)
@@ -137,7 +157,7 @@ __device__ __forceinline__ void slice_read_row(const Slice& s, int lane, float (
 // sequences of the warp naming the same row is the usual Hogwild race (last store wins).
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void coop_visits(const ModelDev& m, const Table& tb, uint32_t neg, uint32_t out, uint32_t fl, int lane,
-                                            const Slice& gh, const Slice& dx, const OptCfg& o) {
+                                            const Slice& gh, const Slice& dx, const OptCfg& o, const bool nostore = false, const bool noatom = false) {
     const int rl = lane & 7, ch = lane >> 3;
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
@@ -149,6 +169,54 @@ __device__ __forceinline__ void coop_visits(const ModelDev& m, const Table& tb, 
             const uint32_t idn = __shfl_sync(kFull, neg, row), ido = __shfl_sync(kFull, out, row);
             f[gg] = __shfl_sync(kFull, fl, row);
             rn[gg] = trec(m, tb, idn) + ch * 4; ro[gg] = trec(m, tb, ido) + ch * 4;
+        }
+        const bool atomics = !o.adam && !noatom;
+        if (atomics) {
+            // ---- Adagrad through L2 atomics: {ld w, atom G += sum g^2} -> sequential applications -> red w, red G ----
+            float4 gn[4], go[4];   // sum of squared raw gradients of the visit (what the atom adds up front)
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int gg = it >> 1, hf = it & 1;
+                const uint32_t off = (uint32_t)(pass * 2 + gg) * 1024u + (uint32_t)(ch + 4 * hf) * 128u + (uint32_t)rl * 16u;
+                const float4 g4 = *reinterpret_cast<const float4*>(gh.p + off);
+                const float4 s4 = sq4(g4);
+                if (f[gg] & 1u) {
+                    gn[it] = s4;
+                    wn[it] = __ldcg(reinterpret_cast<const float4*>(rn[gg] + hf * 16));
+                    sn[it] = atom_add4(rn[gg] + hf * 16 + kD, s4);
+                }
+                if (f[gg] & 2u) {
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (f[gg] & 4u) t = sq4(*reinterpret_cast<const float4*>(dx.p + off));
+                    if (f[gg] & 8u) t = add4(t, s4);
+                    if (f[gg] & 16u) t = add4(t, s4);
+                    go[it] = t;
+                    wo[it] = __ldcg(reinterpret_cast<const float4*>(ro[gg] + hf * 16));
+                    so[it] = atom_add4(ro[gg] + hf * 16 + kD, t);
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int gg = it >> 1, hf = it & 1;
+                const uint32_t off = (uint32_t)(pass * 2 + gg) * 1024u + (uint32_t)(ch + 4 * hf) * 128u + (uint32_t)rl * 16u;
+                const float4 g4 = *reinterpret_cast<const float4*>(gh.p + off);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (f[gg] & 1u) {
+                    const float4 w0 = wn[it], G0 = sn[it];
+                    apply4(wn[it], sn[it], v, g4, 1.0f, o);
+                    red_add4(rn[gg] + hf * 16, sub4(wn[it], w0));
+                    if (o.l2 != 0.0f) red_add4(rn[gg] + hf * 16 + kD, sub4(sub4(sn[it], G0), gn[it]));
+                }
+                if (f[gg] & 2u) {
+                    const float4 w0 = wo[it], G0 = so[it];
+                    if (f[gg] & 4u) { const float4 d4 = *reinterpret_cast<const float4*>(dx.p + off); apply4(wo[it], so[it], v, d4, 1.0f, o); }
+                    if (f[gg] & 8u) apply4(wo[it], so[it], v, g4, 1.0f, o);
+                    if (f[gg] & 16u) apply4(wo[it], so[it], v, g4, -1.0f, o);
+                    red_add4(ro[gg] + hf * 16, sub4(wo[it], w0));
+                    if (o.l2 != 0.0f) red_add4(ro[gg] + hf * 16 + kD, sub4(sub4(so[it], G0), go[it]));
+                }
+            }
+            continue;
         }
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -171,8 +239,10 @@ __device__ __forceinline__ void coop_visits(const ModelDev& m, const Table& tb, 
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (o.adam) v = __ldcg(reinterpret_cast<const float4*>(rn[gg] + hf * 16 + 2 * kD));
                 apply4(wn[it], sn[it], v, g4, 1.0f, o);
+                if (!nostore) {
                 __stcg(reinterpret_cast<float4*>(rn[gg] + hf * 16), wn[it]);
                 __stcg(reinterpret_cast<float4*>(rn[gg] + hf * 16 + kD), sn[it]);
+                } else if (wn[it].x == 12345.678f && sn[it].y == 1.2345f) __stcg(reinterpret_cast<float4*>(rn[gg] + hf * 16), wn[it]);
                 if (o.adam) __stcg(reinterpret_cast<float4*>(rn[gg] + hf * 16 + 2 * kD), v);
             }
             if (f[gg] & 2u) {
@@ -184,8 +254,10 @@ __device__ __forceinline__ void coop_visits(const ModelDev& m, const Table& tb, 
                 }
                 if (f[gg] & 8u) apply4(wo[it], so[it], v, g4, 1.0f, o);
                 if (f[gg] & 16u) apply4(wo[it], so[it], v, g4, -1.0f, o);
+                if (!nostore) {
                 __stcg(reinterpret_cast<float4*>(ro[gg] + hf * 16), wo[it]);
                 __stcg(reinterpret_cast<float4*>(ro[gg] + hf * 16 + kD), so[it]);
+                } else if (wo[it].x == 12345.678f && so[it].y == 1.2345f) __stcg(reinterpret_cast<float4*>(ro[gg] + hf * 16), wo[it]);
                 if (o.adam) __stcg(reinterpret_cast<float4*>(ro[gg] + hf * 16 + 2 * kD), v);
             }
         }
@@ -619,17 +691,32 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                     const uint32_t fl = (act && !triple ? 1u : 0u) | ((act || has_dx) ? 2u : 0u) | (has_dx ? 4u : 0u) | (triple ? 8u : 0u) | (act ? 16u : 0u);
                     float4* rn = bias_rec(m, neg); float4* ro = bias_rec(m, out);
                     float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
-                    if (act) { ba = __ldcg(rn); if (neg != out) bb = __ldcg(ro); }
-                    coop_visits(m, tb, neg, out, fl, lane, SZ0, SZ1, o);
-                    if (act) {   // b[neg] += step(+g), b[out] += step(-g)
+                    const bool bv = act && !(pl.dbg_flags & 4);
+                    const bool batom = !o.adam && !(pl.dbg_flags & 8);
+                    float* fn_ = reinterpret_cast<float*>(rn); float* fo_ = reinterpret_cast<float*>(ro);
+                    if (bv) {
+                        if (batom) {   // {ld b, atom G_b += g^2}: b[neg] takes +g; b[out] takes -g (two entries on one record when neg == out)
+                            ba.x = __ldcg(fn_); ba.y = atomicAdd(fn_ + 1, neg != out ? g * g : 2.0f * g * g);
+                            if (neg != out) { bb.x = __ldcg(fo_); bb.y = atomicAdd(fo_ + 1, g * g); }
+                        } else { ba = __ldcg(rn); if (neg != out) bb = __ldcg(ro); }
+                    }
+                    coop_visits(m, tb, neg, out, (pl.dbg_flags & 1) ? 0u : fl, lane, SZ0, SZ1, o, (pl.dbg_flags & 2) != 0, (pl.dbg_flags & 8) != 0);
+                    if (bv) {   // b[neg] += step(+g), b[out] += step(-g)
+                        const float4 a0 = ba, b0 = bb;
                         if (neg != out) {
                             if (!o.adam) { adagrad1(ba.x, ba.y, g, o.lr, o.l2); adagrad1(bb.x, bb.y, -g, o.lr, o.l2); }
                             else { adam1(ba.x, ba.y, ba.z, g, o); adam1(bb.x, bb.y, bb.z, -g, o); }
-                            __stcg(rn, ba); __stcg(ro, bb);
+                            if (batom) {
+                                atomicAdd(fn_, ba.x - a0.x); atomicAdd(fo_, bb.x - b0.x);
+                                if (o.l2 != 0.0f) { atomicAdd(fn_ + 1, ba.y - a0.y - g * g); atomicAdd(fo_ + 1, bb.y - b0.y - g * g); }
+                            } else { __stcg(rn, ba); __stcg(ro, bb); }
                         } else {
                             if (!o.adam) { adagrad1(ba.x, ba.y, g, o.lr, o.l2); adagrad1(ba.x, ba.y, -g, o.lr, o.l2); }
                             else { adam1(ba.x, ba.y, ba.z, g, o); adam1(ba.x, ba.y, ba.z, -g, o); }
-                            __stcg(rn, ba);
+                            if (batom) {
+                                atomicAdd(fn_, ba.x - a0.x);
+                                if (o.l2 != 0.0f) atomicAdd(fn_ + 1, ba.y - a0.y - 2.0f * g * g);
+                            } else __stcg(rn, ba);
                         }
                     }
                 }

@@ -768,6 +768,8 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
         const char* gen = getenv("SBR_LSTM_TC");
         if (gen && !strcmp(gen, "2")) *err = launch_lstm_tc2(m, p, nt, false, st);
         else if (gen && !strcmp(gen, "2f")) *err = launch_lstm_tc2(m, p, nt, true, st);
+        else if (gen && !strcmp(gen, "3")) *err = launch_lstm_tc3(m, p, nt, 2, st);
+        else if (gen && !strcmp(gen, "34")) *err = launch_lstm_tc3(m, p, nt, 4, st);
         else *err = launch_lstm_tc(m, p, nt, st);
         return 1;
     } else {
