@@ -23,6 +23,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdio>
+
 #include "engine.h"
 #include "tc_tile.cuh"
 
@@ -279,8 +281,13 @@ struct ActB {
     float4 h0, h1;                  // h_t fp32
 };
 
-template <int NT, bool FASTM>
+// TIMING: a debug instantiation in which thread 0 of CTA 0 prints clock64() deltas between the phases of one timestep
+template <int NT, bool FASTM, bool TIMING>
 __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m, PlanDev pl) {
+    long long tk[24];
+    auto tick = [&](int i) { if (TIMING) tk[i] = clock64(); };
+#pragma unroll
+    for (int i = 0; i < 24; ++i) tk[i] = 0;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* Wt = smem + OFF_WT;
     uint8_t* Wb = smem + OFF_WB;
@@ -438,8 +445,10 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
 #pragma unroll
                 for (int j = 0; j < 5; ++j) cand[j] = j < tries ? draw_item(key, step, (uint32_t)t, (uint32_t)j, pl.neg_range) : 0u;
                 // ---- x_t has landed in SD1 (issued a step ago) ----
+                tick(0);
                 cp_wait<0>();
                 __syncwarp();
+                tick(1);
                 {
                     float x[32];
                     slice_read_row(SD1, lane, x);
@@ -466,7 +475,9 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                 }
                 fence_async_smem();
                 tc_fence_before_sync();
+                tick(2);
                 tile_bar(tile);
+                tick(3);
                 if (r == 0) {
                     tc_fence_after_sync();
 #pragma unroll
@@ -478,8 +489,10 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                 const float bp = act ? __ldcg(reinterpret_cast<const float*>(bias_rec(m, out))) : 0.0f;
 #pragma unroll
                 for (int j = 0; j < 5; ++j) bc[j] = (j < tries && act) ? __ldcg(reinterpret_cast<const float*>(bias_rec(m, cand[j]))) : 0.0f;
+                tick(4);
                 mbar_wait(mbar + tile, phase); phase ^= 1;
                 tc_fence_after_sync();
+                tick(5);
                 // the tf32 Z tile is idle until the next step: candidates 2 and 3 go there (G2)
                 if (tries > 2) { gather_async(m, tb, cand[2], lane, SZ0); gather_async(m, tb, cand[3], lane, SZ1); }
                 cp_commit();
@@ -511,9 +524,11 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                     }
                 }
                 tc_fence_before_sync();  // TMEM reads ordered before the next MMA (issued after the next tile barrier)
+                tick(6);
                 // scoring + negative sampling (sequence_model.rs:47-68, lstm.rs:300-320)
                 cp_wait<1>();            // G1 (target, candidates 0 and 1) has landed; G2 may still fly
                 __syncwarp();
+                tick(7);
                 float pos = bp;
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
@@ -536,6 +551,7 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                         if (1.0f - pos + ngs > 0.0f) done = true;
                     }
                 };
+                tick(8);
                 bool alld = __all_sync(kFull, done);
                 if (!alld) { score(SD1, cand[0], bc[0]); __syncwarp(); }
                 // x_{t+1} = E[ids[t+1]] takes the slice candidate 0 just left (G3)
@@ -563,6 +579,7 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                         score(SB, cand[4], bc[4]);
                     }
                 }
+                tick(9);
                 if (act) {
                     float l, g;
                     if (m.loss == 0) { const float s = sigm<FASTM>(ngs - pos); l = s; g = s * (1.0f - s); }
@@ -578,6 +595,10 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                     G_[(size_t)t * gstride] = g; NEG[(size_t)t * gstride] = neg;
                 }
                 __syncwarp();            // every lane is done with SD0 before the next step's target row overwrites it
+                tick(10);
+                if (TIMING && blockIdx.x == 0 && tid == 0 && it == 1 && (t == 10 || t == 11))
+                    printf("FWD t=%d: wait_x %lld | Zt+scratch %lld | tile_bar %lld | mma_issue+bias_ld %lld | mma_wait %lld | gates %lld | wait_p %lld | pos %lld | tries %lld | loss+dq %lld | total %lld\n",
+                           t, tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[7] - tk[6], tk[8] - tk[7], tk[9] - tk[8], tk[10] - tk[9], tk[10] - tk[0]);
                 idA = idB; idB = idC; idC = idD;
             }
             cp_wait<0>();
@@ -606,8 +627,10 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                 float g_n = 0.0f; uint32_t neg_n = 0, out_n = 0;
                 if (actn) { g_n = G_[(size_t)(t - 1) * gstride]; neg_n = NEG[(size_t)(t - 1) * gstride]; out_n = __ldg(ids + t); }
                 else if (t == 0 && Tn > 0) out_n = __ldg(ids);   // out_{-1} = ids[0] = in_0
+                tick(12);
                 if (t >= 1) prefetch_step(t - 1);
                 if (prev_valid) { mbar_wait(mbar + tile, phase); phase ^= 1; tc_fence_after_sync(); }
+                tick(13);
                 if (t >= 0) {
                     stage_z_async(t, act);   // the previous MMA is done with the Z tile
 #pragma unroll
@@ -655,10 +678,13 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                         *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 12 + db, 16)) = pack_bf16x8(dO);
                         if (db < 3) cur = nxt;
                     }
+                    tick(14);
                     cp_wait<0>();             // Z_t rows have landed
                     fence_async_smem();
                     tc_fence_before_sync();   // also orders this thread's TMEM reads of dz_{t+1} before the MMA that overwrites them
+                    tick(15);
                     tile_bar(tile);
+                    tick(16);
                     if (r == 0) {
                         tc_fence_after_sync();
 #pragma unroll
@@ -684,6 +710,7 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                     tc_fence_before_sync();
                 }
                 __syncwarp();            // the g h_t and dx_{t+1} slices are complete
+                tick(17);
                 // ---- sparse visits of this timestep (overlap the MMAs): E[neg_t]; E[out_t] with the deferred E[in_{t+1}] ----
                 {
                     const bool triple = act && neg == out;
@@ -720,6 +747,10 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                         }
                     }
                 }
+                tick(18);
+                if (TIMING && blockIdx.x == 0 && tid == 0 && it == 1 && (t == 10 || t == 11))
+                    printf("BWD t=%d: scalars+prefetch+mma_wait %lld | deltas(4 blocks) %lld | wait_z %lld | tile_bar %lld | mma_issue+preload %lld | visits %lld | total %lld\n",
+                           t, tk[13] - tk[12], tk[14] - tk[13], tk[15] - tk[14], tk[16] - tk[15], tk[17] - tk[16], tk[18] - tk[17], tk[18] - tk[12]);
                 prev_valid = true; prev_act = act;
                 g_c = g_n; neg_c = neg_n; out_c = out_n;
             }
@@ -789,20 +820,21 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
     if (tid < 32) tmem_dealloc<(NT == 1 ? 256 : 512)>(*tmem_ptr);
 }
 
-template <int NT, bool FASTM>
+template <int NT, bool FASTM, bool TIMING = false>
 cudaError_t launch_one(const ModelDev& m, const PlanDev& p, cudaStream_t st) {
     const size_t smem = OFF_TILES + (size_t)NT * TILE_BYTES;
     const int per_cta = 128 * NT;
     dim3 grid((p.P + per_cta - 1) / per_cta);
-    cudaError_t e = cudaFuncSetAttribute(lstm_tc2_train_kernel<NT, FASTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(lstm_tc2_train_kernel<NT, FASTM, TIMING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    lstm_tc2_train_kernel<NT, FASTM><<<grid, per_cta, smem, st>>>(m, p);
+    lstm_tc2_train_kernel<NT, FASTM, TIMING><<<grid, per_cta, smem, st>>>(m, p);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t launch_lstm_tc2(const ModelDev& m, const PlanDev& p, int nt, bool fast_math, cudaStream_t st) {
+    if (nt == 2 && (p.dbg_flags & 16)) return launch_one<2, false, true>(m, p, st);
     if (nt == 2) return fast_math ? launch_one<2, true>(m, p, st) : launch_one<2, false>(m, p, st);
     return fast_math ? launch_one<1, true>(m, p, st) : launch_one<1, false>(m, p, st);
 }

@@ -70,6 +70,26 @@ __device__ __forceinline__ void apply4(float4& w, float4& s, float4& v, const fl
     }
 }
 
+// L2 atomics for the Hogwild Adagrad visits (see kernels_lstm_tc2.cu): {ld w, atom G += sum g^2} in one round trip, the
+// sequential applications in registers from the returned G, then fire-and-forget reductions on w and G.
+__device__ __forceinline__ float4 atom_add4(float* p, const float4& v) {
+    float4 o;
+    asm volatile("atom.global.add.v4.f32 {%0, %1, %2, %3}, [%4], {%5, %6, %7, %8};"
+                 : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    return o;
+}
+__device__ __forceinline__ void red_add4(float* p, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 sq4(const float4& a) { return make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w); }
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 sub4(const float4& a, const float4& b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+// word `pr` (bf16 elements 2 pr, 2 pr + 1) of a packed block; the two halves as floats
+__device__ __forceinline__ uint32_t word_of(const uint4& u, int pr) { return pr == 0 ? u.x : pr == 1 ? u.y : pr == 2 ? u.z : u.w; }
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) { uint32_t o; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(hi), "f"(lo)); return o; }
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -178,8 +198,8 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
     constexpr int kStepU4 = (8 + 36) * 128;
     uint4* sbase = reinterpret_cast<uint4*>(pl.scratch);
     float* G_ = reinterpret_cast<float*>(sbase + (size_t)T * ntiles * kStepU4) + (size_t)tile_gid * 128 + r;   // + t * gstride
-    uint32_t* NEG = reinterpret_cast<uint32_t*>(G_ + (size_t)T * ntiles * 128);
     const size_t gstride = ntiles * 128;
+#define NEG (reinterpret_cast<uint32_t*>(G_ + (size_t)T * gstride))
     enum { AF = 0, AI = 1, AG = 2, AO = 3, AX = 4, ADQ = 5, AC = 6, ATC = 7, AHB = 8 };
     auto step_base = [&](int t) -> uint4* { return sbase + ((size_t)t * ntiles + tile_gid) * kStepU4; };
     auto sf4 = [&](int t, int c4) -> float4* { return reinterpret_cast<float4*>(step_base(t) + (size_t)c4 * 128 + r); };
@@ -218,6 +238,7 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
     };
     // The sparse visits of one backward timestep, this warp's chunks of the 32 rows (flags as in kernels_lstm_tc2.cu):
     //   bit 0: E[neg] += step(+g h)      bit 1: visit E[out]: [bit 2: step(dx_{t+1})] [bit 3: step(+g h)] [bit 4: step(-g h)]
+    const bool noatom = (pl.dbg_flags & 8) != 0;
     auto coop_visits = [&](uint32_t neg, uint32_t out, uint32_t fl, const Slice& gh, const Slice& dx, const OptCfg& o) {
         const int rl = lane % RPI, ch = lane / RPI;
         constexpr int GPP = NGI >= 2 ? 2 : 1;   // row groups per pass: 4 row visits (w, s each) in flight
@@ -232,6 +253,47 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                 f[gg] = __shfl_sync(kFull, fl, row);
                 rn[gg] = trec(m, tb, idn) + part * DPT + ch * 4; ro[gg] = trec(m, tb, ido) + part * DPT + ch * 4;
                 off[gg] = (uint32_t)(row >> 3) * GS + (uint32_t)ch * 128u + (uint32_t)(row & 7) * 16u;
+            }
+            if (!o.adam && !noatom) {
+                float4 gn[GPP], go[GPP];   // what the atom added up front: sum of squared raw gradients
+#pragma unroll
+                for (int gg = 0; gg < GPP; ++gg) {
+                    const float4 s4 = sq4(*reinterpret_cast<const float4*>(gh.p + off[gg]));
+                    if (f[gg] & 1u) {
+                        gn[gg] = s4;
+                        wn[gg] = __ldcg(reinterpret_cast<const float4*>(rn[gg]));
+                        sn[gg] = atom_add4(rn[gg] + kD, s4);
+                    }
+                    if (f[gg] & 2u) {
+                        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (f[gg] & 4u) t4 = sq4(*reinterpret_cast<const float4*>(dx.p + off[gg]));
+                        if (f[gg] & 8u) t4 = add4(t4, s4);
+                        if (f[gg] & 16u) t4 = add4(t4, s4);
+                        go[gg] = t4;
+                        wo[gg] = __ldcg(reinterpret_cast<const float4*>(ro[gg]));
+                        so[gg] = atom_add4(ro[gg] + kD, t4);
+                    }
+                }
+#pragma unroll
+                for (int gg = 0; gg < GPP; ++gg) {
+                    const float4 g4 = *reinterpret_cast<const float4*>(gh.p + off[gg]);
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (f[gg] & 1u) {
+                        const float4 w0 = wn[gg], G0 = sn[gg];
+                        apply4(wn[gg], sn[gg], v, g4, 1.0f, o);
+                        red_add4(rn[gg], sub4(wn[gg], w0));
+                        if (o.l2 != 0.0f) red_add4(rn[gg] + kD, sub4(sub4(sn[gg], G0), gn[gg]));
+                    }
+                    if (f[gg] & 2u) {
+                        const float4 w0 = wo[gg], G0 = so[gg];
+                        if (f[gg] & 4u) { const float4 d4 = *reinterpret_cast<const float4*>(dx.p + off[gg]); apply4(wo[gg], so[gg], v, d4, 1.0f, o); }
+                        if (f[gg] & 8u) apply4(wo[gg], so[gg], v, g4, 1.0f, o);
+                        if (f[gg] & 16u) apply4(wo[gg], so[gg], v, g4, -1.0f, o);
+                        red_add4(ro[gg], sub4(wo[gg], w0));
+                        if (o.l2 != 0.0f) red_add4(ro[gg] + kD, sub4(sub4(so[gg], G0), go[gg]));
+                    }
+                }
+                continue;
             }
 #pragma unroll
             for (int gg = 0; gg < GPP; ++gg) {
@@ -298,15 +360,15 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
     const bool issuer = tt == 0;
     uint32_t phase = 0;
 
-    XorShift rng; rng.x = rng.y = rng.z = rng.w = 1; uint64_t key = 0; uint32_t* ord = nullptr;
+    uint64_t key = 0; uint32_t* ord = nullptr;
     uint64_t step = pl.step_ctr[live ? p : 0];
-    if (live) { rng = pl.rng[p]; key = pl.keys[p]; ord = pl.order + (size_t)p * pl.n; }
-    float loss_acc = 0.0f; unsigned long long ex = 0;
+    if (live) { key = pl.keys[p]; ord = pl.order + (size_t)p * pl.n; }
     OptCfg o; o.lr = m.lr; o.l2 = m.l2; o.adam = m.opt == 1; o.c1 = 1.0f; o.c2 = 1.0f;
     const int tries = m.loss == 2 ? 5 : 1;
 
     for (int ep = 0; ep < pl.epochs; ++ep) {
         if (live && lead) {  // thread_rng.shuffle(partition)  sequence_model.rs:109
+            XorShift rng = pl.rng[p];
             uint32_t i = pl.n;
             while (i >= 2) {
                 i -= 1;
@@ -314,6 +376,7 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                 const uint32_t a = ord[i], b = ord[j];
                 ord[i] = b; ord[j] = a;
             }
+            pl.rng[p] = rng;
         }
         quad_bar();   // the other owners read the shuffled order (same SM: visible after the barrier)
         for (uint32_t it = 0; it < pl.n; ++it, ++step) {
@@ -346,9 +409,8 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                 const uint32_t out = act ? idB : 0u;
                 uint32_t idD = 0;
                 if (t + 3 <= Tn) idD = __ldg(ids + t + 3);
-                uint32_t cand[5]; float bc[5];
-#pragma unroll
-                for (int j = 0; j < 5; ++j) cand[j] = j < tries ? draw_item(key, step, (uint32_t)t, (uint32_t)j, pl.neg_range) : 0u;
+                float bc[5];
+                auto cand = [&](int j) -> uint32_t { return draw_item(key, step, (uint32_t)t, (uint32_t)j, pl.neg_range); };
                 // ---- x_t has landed in SD1 (issued a step ago) ----
                 cp_wait<0>();
                 __syncwarp();
@@ -362,8 +424,8 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                     __syncwarp();
                     // target row and the first candidates of this step: G1
                     gather_async(out, SD0);
-                    gather_async(cand[0], SD1);
-                    if (tries > 1) gather_async(cand[1], SB);
+                    gather_async(cand(0), SD1);
+                    if (tries > 1) gather_async(cand(1), SB);
                     cp_commit();
 #pragma unroll
                     for (int cc = 0; cc < NCH; ++cc) {
@@ -397,12 +459,12 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                 if (lead && act) {
                     bp = __ldcg(reinterpret_cast<const float*>(bias_rec(m, out)));
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) if (j < tries) bc[j] = __ldcg(reinterpret_cast<const float*>(bias_rec(m, cand[j])));
+                    for (int j = 0; j < 5; ++j) if (j < tries) bc[j] = __ldcg(reinterpret_cast<const float*>(bias_rec(m, cand(j))));
                 }
                 mbar_wait(mbar + tile, phase); phase ^= 1;
                 tc_fence_after_sync();
                 // the tf32 Z tile is idle until the next step: candidates 2 and 3 go there (G2)
-                if (tries > 2) { gather_async(cand[2], SZ0); gather_async(cand[3], SZ1); }
+                if (tries > 2) { gather_async(cand(2), SZ0); gather_async(cand(3), SZ1); }
                 cp_commit();
 #pragma unroll
                 for (int b = 0; b < NB8; ++b) {
@@ -470,30 +532,30 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                     }
                 };
                 bool alld = __all_sync(kFull, done);   // identical in the DS warps of a quad: same lanes, same decisions
-                if (!alld) { score(SD1, cand[0], bc[0]); __syncwarp(); }
+                if (!alld) { score(SD1, cand(0), bc[0]); __syncwarp(); }
                 // x_{t+1} = E[ids[t+1]] takes the slice candidate 0 just left (G3)
                 if (t + 1 < Tmax) gather_async((t + 1 < Tn) ? idB : 0u, SD1);
                 cp_commit();
                 if (tries > 1) {
                     alld = __all_sync(kFull, done);
                     if (!alld) {
-                        score(SB, cand[1], bc[1]);
+                        score(SB, cand(1), bc[1]);
                         __syncwarp();
-                        gather_async(cand[4], SB);   // candidate 4 takes candidate 1's slice (G4)
+                        gather_async(cand(4), SB);   // candidate 4 takes candidate 1's slice (G4)
                         cp_commit();
                         alld = __all_sync(kFull, done);
                     }
                     if (!alld) {
                         cp_wait<2>();   // G2 (candidates 2, 3) landed; G3, G4 may fly
                         __syncwarp();
-                        score(SZ0, cand[2], bc[2]);
+                        score(SZ0, cand(2), bc[2]);
                         alld = __all_sync(kFull, done);
                     }
-                    if (!alld) { score(SZ1, cand[3], bc[3]); alld = __all_sync(kFull, done); }
+                    if (!alld) { score(SZ1, cand(3), bc[3]); alld = __all_sync(kFull, done); }
                     if (!alld) {
                         cp_wait<0>();
                         __syncwarp();
-                        score(SB, cand[4], bc[4]);
+                        score(SB, cand(4), bc[4]);
                     }
                 }
                 if (act) {
@@ -548,8 +610,7 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
 #pragma unroll
                     for (int b = 0; b < NB8; ++b) {
                         const int gb = gb0 + b;
-                        ActB nxt;
-                        if (b + 1 < NB8) load_act(nxt, t, gb + 1, act);
+                        if (b > 0) load_act(cur, t, gb, act);   // (no double buffering: 128 registers per thread)
                         float dhv[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) dhv[e] = 0.0f;
@@ -562,34 +623,40 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                             slice_st(SZ1, 2 * b, make_float4(__uint_as_float(rb[0]), __uint_as_float(rb[1]), __uint_as_float(rb[2]), __uint_as_float(rb[3])));
                             slice_st(SZ1, 2 * b + 1, make_float4(__uint_as_float(rb[4]), __uint_as_float(rb[5]), __uint_as_float(rb[6]), __uint_as_float(rb[7])));
                         }
-                        float df[8], di[8], dg[8], dO[8];
-                        float f8[8], i8[8], g8[8], o8[8], q8[8], cp8[8], tc8[8];
-                        unpack8(cur.f, f8); unpack8(cur.i, i8); unpack8(cur.g, g8); unpack8(cur.o, o8); unpack8(cur.q, q8);
-                        unpack8(cur.cp, cp8); unpack8(cur.tc, tc8);
                         // gradient of the two rows that only need h_t goes straight to the staging slice
                         slice_st(SZ0, 2 * b, make_float4(g * cur.h0.x, g * cur.h0.y, g * cur.h0.z, g * cur.h0.w));
                         slice_st(SZ0, 2 * b + 1, make_float4(g * cur.h1.x, g * cur.h1.y, g * cur.h1.z, g * cur.h1.w));
+                        uint32_t wdf[4], wdi[4], wdg[4], wdo[4];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int d = b * 8 + e;
-                            const float tcv = tc8[e];
-                            const float dh = dhv[e] + q8[e];
-                            const float d_o = dh * tcv;
-                            const float dc = dc_rec[d] + dh * o8[e] * (1.0f - tcv * tcv);
-                            float d_f = dc * cp8[e], d_i = dc * g8[e];
-                            const float d_g = dc * i8[e];
-                            dc_rec[d] = act ? dc * f8[e] : 0.0f;
-                            if (coupled) { d_f -= d_i; d_i = 0.0f; }
-                            df[e] = d_f * f8[e] * (1.0f - f8[e]);
-                            di[e] = coupled ? 0.0f : d_i * i8[e] * (1.0f - i8[e]);
-                            dg[e] = d_g * (1.0f - g8[e] * g8[e]);
-                            dO[e] = d_o * o8[e] * (1.0f - o8[e]);
+                        for (int pr = 0; pr < 4; ++pr) {   // two hidden units at a time, straight from / to packed bf16 words
+                            const uint32_t uf = word_of(cur.f, pr), ui = word_of(cur.i, pr), ug = word_of(cur.g, pr), uo = word_of(cur.o, pr);
+                            const uint32_t uq = word_of(cur.q, pr), ucp = word_of(cur.cp, pr), utc = word_of(cur.tc, pr);
+                            float rdf[2], rdi[2], rdg[2], rdo[2];
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const int e = 2 * pr + k, d = b * 8 + e;
+                                const float f_ = k ? bf_hi(uf) : bf_lo(uf), i_ = k ? bf_hi(ui) : bf_lo(ui), g_ = k ? bf_hi(ug) : bf_lo(ug);
+                                const float o_ = k ? bf_hi(uo) : bf_lo(uo), q_ = k ? bf_hi(uq) : bf_lo(uq);
+                                const float cp_ = k ? bf_hi(ucp) : bf_lo(ucp), tcv = k ? bf_hi(utc) : bf_lo(utc);
+                                const float dh = dhv[e] + q_;
+                                const float d_o = dh * tcv;
+                                const float dc = dc_rec[d] + dh * o_ * (1.0f - tcv * tcv);
+                                float d_f = dc * cp_, d_i = dc * g_;
+                                const float d_g = dc * i_;
+                                dc_rec[d] = act ? dc * f_ : 0.0f;
+                                if (coupled) { d_f -= d_i; d_i = 0.0f; }
+                                rdf[k] = d_f * f_ * (1.0f - f_);
+                                rdi[k] = coupled ? 0.0f : d_i * i_ * (1.0f - i_);
+                                rdg[k] = d_g * (1.0f - g_ * g_);
+                                rdo[k] = d_o * o_ * (1.0f - o_);
+                            }
+                            wdf[pr] = pack2(rdf[0], rdf[1]); wdi[pr] = pack2(rdi[0], rdi[1]);
+                            wdg[pr] = pack2(rdg[0], rdg[1]); wdo[pr] = pack2(rdo[0], rdo[1]);
                         }
-                        *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 0 + gb, 16)) = pack_bf16x8(df);
-                        *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 4 + gb, 16)) = pack_bf16x8(di);
-                        *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 8 + gb, 16)) = pack_bf16x8(dg);
-                        *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 12 + gb, 16)) = pack_bf16x8(dO);
-                        if (b + 1 < NB8) cur = nxt;
+                        *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 0 + gb, 16)) = make_uint4(wdf[0], wdf[1], wdf[2], wdf[3]);
+                        *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 4 + gb, 16)) = make_uint4(wdi[0], wdi[1], wdi[2], wdi[3]);
+                        *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 8 + gb, 16)) = make_uint4(wdg[0], wdg[1], wdg[2], wdg[3]);
+                        *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 12 + gb, 16)) = make_uint4(wdo[0], wdo[1], wdo[2], wdo[3]);
                     }
                     cp_wait<0>();             // Z_t rows have landed
                     fence_async_smem();
@@ -628,24 +695,38 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                     float4* rn = bias_rec(m, neg); float4* ro = bias_rec(m, out);
                     float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
                     const bool bv = act && lead;
-                    if (bv) { ba = __ldcg(rn); if (neg != out) bb = __ldcg(ro); }
+                    const bool batom = !o.adam && !noatom;
+                    float* fn_ = reinterpret_cast<float*>(rn); float* fo_ = reinterpret_cast<float*>(ro);
+                    if (bv) {
+                        if (batom) {   // {ld b, atom G_b += g^2}: b[neg] takes +g; b[out] takes -g (two entries on one record when neg == out)
+                            ba.x = __ldcg(fn_); ba.y = atomicAdd(fn_ + 1, neg != out ? g * g : 2.0f * g * g);
+                            if (neg != out) { bb.x = __ldcg(fo_); bb.y = atomicAdd(fo_ + 1, g * g); }
+                        } else { ba = __ldcg(rn); if (neg != out) bb = __ldcg(ro); }
+                    }
                     coop_visits(neg, out, fl, SZ0, SZ1, o);
                     if (bv) {   // b[neg] += step(+g), b[out] += step(-g)
+                        const float4 a0 = ba, b0 = bb;
                         if (neg != out) {
                             if (!o.adam) { adagrad1(ba.x, ba.y, g, o.lr, o.l2); adagrad1(bb.x, bb.y, -g, o.lr, o.l2); }
                             else { adam1(ba.x, ba.y, ba.z, g, o); adam1(bb.x, bb.y, bb.z, -g, o); }
-                            __stcg(rn, ba); __stcg(ro, bb);
+                            if (batom) {
+                                atomicAdd(fn_, ba.x - a0.x); atomicAdd(fo_, bb.x - b0.x);
+                                if (o.l2 != 0.0f) { atomicAdd(fn_ + 1, ba.y - a0.y - g * g); atomicAdd(fo_ + 1, bb.y - b0.y - g * g); }
+                            } else { __stcg(rn, ba); __stcg(ro, bb); }
                         } else {
                             if (!o.adam) { adagrad1(ba.x, ba.y, g, o.lr, o.l2); adagrad1(ba.x, ba.y, -g, o.lr, o.l2); }
                             else { adam1(ba.x, ba.y, ba.z, g, o); adam1(ba.x, ba.y, ba.z, -g, o); }
-                            __stcg(rn, ba);
+                            if (batom) {
+                                atomicAdd(fn_, ba.x - a0.x);
+                                if (o.l2 != 0.0f) atomicAdd(fn_ + 1, ba.y - a0.y - 2.0f * g * g);
+                            } else __stcg(rn, ba);
                         }
                     }
                 }
                 prev_valid = true; prev_act = act;
                 g_c = g_n; neg_c = neg_n; out_c = out_n;
             }
-            if (live && lead) { loss_acc += loss_seq; ex += (unsigned long long)Tn; }
+            if (live && lead) { pl.loss_acc[p] += loss_seq; pl.examples[p] += (unsigned long long)Tn; }
 
             // =========================== dense step on the CTA-summed gradient ===========================
             // TMEM lane gd = r of a tile holds row gd of its dW^T: columns 0..63 = dW[k][gd], column 64 = dbias[gd];
@@ -708,10 +789,7 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
             __syncthreads();
         }
     }
-    if (live && lead) {
-        pl.rng[p] = rng; pl.step_ctr[p] = step;
-        pl.loss_acc[p] += loss_acc; pl.examples[p] += ex;
-    }
+    if (live && lead) pl.step_ctr[p] = step;
     tc_fence_before_sync();
     __syncthreads();
     if (tid < 32) tmem_dealloc<(NT == 1 ? 256 : 512)>(*tmem_ptr);
@@ -727,6 +805,8 @@ cudaError_t launch_one(const ModelDev& m, const PlanDev& p, cudaStream_t st) {
     lstm_tc3_train_kernel<NT, DS><<<grid, seq_per_cta * DS, smem, st>>>(m, p);
     return cudaGetLastError();
 }
+
+#undef NEG
 
 }  // namespace
 

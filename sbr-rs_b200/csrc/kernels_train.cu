@@ -763,14 +763,15 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
             default: *err = cudaErrorInvalidValue; return 0;
         }
     } else if (int nt = lstm_kernel_choice(m, p.P)) {
-        // SBR_LSTM_TC selects the tile-kernel generation: "1" = kernels_lstm_tc.cu, "2" = kernels_lstm_tc2.cu
-        // (prefetching pipeline, exp-based gates), "2f" = the same with MUFU.TANH gates
+        // SBR_LSTM_TC selects the tile-kernel generation (default "3"): "1" = kernels_lstm_tc.cu (thread per sequence),
+        // "2" = kernels_lstm_tc2.cu (+ cp.async prefetch pipeline, merged visits, L2-atomic Adagrad), "2f" = the same
+        // with MUFU.TANH gates, "3" / "34" = kernels_lstm_tc3.cu with 2 / 4 threads per sequence
         const char* gen = getenv("SBR_LSTM_TC");
-        if (gen && !strcmp(gen, "2")) *err = launch_lstm_tc2(m, p, nt, false, st);
+        if (gen && !strcmp(gen, "1")) *err = launch_lstm_tc(m, p, nt, st);
+        else if (gen && !strcmp(gen, "2")) *err = launch_lstm_tc2(m, p, nt, false, st);
         else if (gen && !strcmp(gen, "2f")) *err = launch_lstm_tc2(m, p, nt, true, st);
-        else if (gen && !strcmp(gen, "3")) *err = launch_lstm_tc3(m, p, nt, 2, st);
         else if (gen && !strcmp(gen, "34")) *err = launch_lstm_tc3(m, p, nt, 4, st);
-        else *err = launch_lstm_tc(m, p, nt, st);
+        else *err = launch_lstm_tc3(m, p, nt, 2, st);
         return 1;
     } else {
         dim3 block(kLstmWPC * 32), grid((p.P + kLstmWPC - 1) / kLstmWPC);
