@@ -216,6 +216,75 @@ __device__ __forceinline__ void update_row(float* __restrict__ rec, int lane, co
     }
 }
 
+// ---- Adagrad visits through L2 atomics (Hogwild with more than one partition) ----
+// A visit as load -> compute -> store turns every popular row into a read-modify-write hazard between thousands of
+// concurrent partitions (lost updates, and on B200 a measured 2-3x slow-down on the 1,683-row ML-100K table).  The
+// accumulator is additive, so: {ld w, atom.add G += g^2 (returns the old G)} in one round trip, the Adagrad step in
+// registers from the returned value, then fire-and-forget reductions w += dw and G += (l2 cross terms).
+template <int D>
+__device__ __forceinline__ void row_atom_add(float* __restrict__ p, int lane, const float (&v)[VecOf<D>::V], float (&old)[VecOf<D>::V]) {
+    constexpr int V = VecOf<D>::V;
+    if constexpr (D < 32) {
+        old[0] = lane < D ? atomicAdd(p + lane, v[0]) : 0.0f;
+    } else if constexpr (V == 1) {
+        old[0] = atomicAdd(p + lane, v[0]);
+    } else if constexpr (V == 2) {
+        asm volatile("atom.global.add.v2.f32 {%0, %1}, [%2], {%3, %4};" : "=f"(old[0]), "=f"(old[1]) : "l"(p + 2 * lane), "f"(v[0]), "f"(v[1]) : "memory");
+    } else {
+#pragma unroll
+        for (int j = 0; j < V / 4; ++j)
+            asm volatile("atom.global.add.v4.f32 {%0, %1, %2, %3}, [%4], {%5, %6, %7, %8};"
+                         : "=f"(old[4 * j]), "=f"(old[4 * j + 1]), "=f"(old[4 * j + 2]), "=f"(old[4 * j + 3])
+                         : "l"(p + j * 128 + lane * 4), "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+    }
+}
+template <int D>
+__device__ __forceinline__ void row_red_add(float* __restrict__ p, int lane, const float (&v)[VecOf<D>::V]) {
+    constexpr int V = VecOf<D>::V;
+    if constexpr (D < 32) {
+        if (lane < D) atomicAdd(p + lane, v[0]);
+    } else if constexpr (V == 1) {
+        atomicAdd(p + lane, v[0]);
+    } else if constexpr (V == 2) {
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p + 2 * lane), "f"(v[0]), "f"(v[1]) : "memory");
+    } else {
+#pragma unroll
+        for (int j = 0; j < V / 4; ++j)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + j * 128 + lane * 4), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                         "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+    }
+}
+// the register part of an atomic visit: from w and the G returned by the atom (which already added q = g^2) to the deltas
+__device__ __forceinline__ void adagrad_atomic_elem(float w, float Gold, float g, float q, float lr, float l2, float& dw, float& dG) {
+    const float gg = g + w * l2;
+    const float Gn = Gold + gg * gg;
+    dw = -(lr / (1e-10f + sqrtf(Gn)) * gg);
+    dG = Gn - Gold - q;
+}
+template <int D>
+__device__ __forceinline__ void update_row_atomic(float* __restrict__ rec, int lane, const float (&g)[VecOf<D>::V], const OptCfg& o) {
+    constexpr int V = VecOf<D>::V;
+    float w[V], q[V], Gold[V], dw[V], dG[V];
+    row_load_cg<D>(rec, lane, w);
+#pragma unroll
+    for (int v = 0; v < V; ++v) q[v] = g[v] * g[v];
+    row_atom_add<D>(rec + D, lane, q, Gold);
+#pragma unroll
+    for (int v = 0; v < V; ++v) adagrad_atomic_elem(w[v], Gold[v], g[v], q[v], o.lr, o.l2, dw[v], dG[v]);
+    row_red_add<D>(rec, lane, dw);
+    if (o.l2 != 0.0f) row_red_add<D>(rec + D, lane, dG);
+}
+__device__ __forceinline__ void update_bias_atomic(float4* __restrict__ rec, float g, const OptCfg& o) {
+    float* f = reinterpret_cast<float*>(rec);
+    const float q = g * g;
+    const float b = __ldcg(f);
+    const float Gold = atomicAdd(f + 1, q);
+    float db, dG;
+    adagrad_atomic_elem(b, Gold, g, q, o.lr, o.l2, db, dG);
+    atomicAdd(f, db);
+    if (o.l2 != 0.0f) atomicAdd(f + 1, dG);
+}
+
 // bias record: [b, s1, s2, pad] (float4) -- one lane does the visit
 __device__ __forceinline__ void update_bias(float4* __restrict__ rec, float g, const OptCfg& o) {
     float4 r = __ldcg(rec);

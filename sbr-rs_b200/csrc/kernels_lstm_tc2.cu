@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                     float4* rn = bias_rec(m, neg); float4* ro = bias_rec(m, out);
                     float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
                     const bool bv = act && !(pl.dbg_flags & 4);
-                    const bool batom = !o.adam && !(pl.dbg_flags & 8);
+                    const bool batom = !o.adam && !(pl.dbg_flags & 8) && !m.hbm_resident;
                     float* fn_ = reinterpret_cast<float*>(rn); float* fo_ = reinterpret_cast<float*>(ro);
                     if (bv) {
                         if (batom) {   // {ld b, atom G_b += g^2}: b[neg] takes +g; b[out] takes -g (two entries on one record when neg == out)
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                             if (neg != out) { bb.x = __ldcg(fo_); bb.y = atomicAdd(fo_ + 1, g * g); }
                         } else { ba = __ldcg(rn); if (neg != out) bb = __ldcg(ro); }
                     }
-                    coop_visits(m, tb, neg, out, (pl.dbg_flags & 1) ? 0u : fl, lane, SZ0, SZ1, o, (pl.dbg_flags & 2) != 0, (pl.dbg_flags & 8) != 0);
+                    coop_visits(m, tb, neg, out, (pl.dbg_flags & 1) ? 0u : fl, lane, SZ0, SZ1, o, (pl.dbg_flags & 2) != 0, (pl.dbg_flags & 8) != 0 || m.hbm_resident != 0);
                     if (bv) {   // b[neg] += step(+g), b[out] += step(-g)
                         const float4 a0 = ba, b0 = bb;
                         if (neg != out) {

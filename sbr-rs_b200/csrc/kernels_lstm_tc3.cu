@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
     };
     // The sparse visits of one backward timestep, this warp's chunks of the 32 rows (flags as in kernels_lstm_tc2.cu):
     //   bit 0: E[neg] += step(+g h)      bit 1: visit E[out]: [bit 2: step(dx_{t+1})] [bit 3: step(+g h)] [bit 4: step(-g h)]
-    const bool noatom = (pl.dbg_flags & 8) != 0;
+    const bool noatom = (pl.dbg_flags & 8) != 0 || m.hbm_resident != 0;   // hot rows only exist on L2-resident tables
     auto coop_visits = [&](uint32_t neg, uint32_t out, uint32_t fl, const Slice& gh, const Slice& dx, const OptCfg& o) {
         const int rl = lane % RPI, ch = lane / RPI;
         constexpr int GPP = NGI >= 2 ? 2 : 1;   // row groups per pass: 4 row visits (w, s each) in flight

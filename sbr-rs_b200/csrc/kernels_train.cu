@@ -113,6 +113,9 @@ __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl)
     uint32_t* ord = pl.order + (size_t)p * pl.n;
     float loss_acc = 0.0f; unsigned long long ex = 0;
     OptCfg o; o.lr = m.lr; o.l2 = m.l2; o.adam = m.opt == 1; o.c1 = 1.0f; o.c2 = 1.0f;
+    // Hogwild with more than one partition: Adagrad visits go through L2 atomics (common.cuh); one partition keeps
+    // the plain load / store visit, which is the reference's single-thread arithmetic to the last bit
+    const bool atomics = !o.adam && pl.P > 1 && !m.hbm_resident && !(pl.dbg_flags & 8);   // (HBM-resident tables: no hot rows, plain visits are 8 % faster)
 
     for (int ep = 0; ep < pl.epochs; ++ep) {
         if (lane == 0) shuffle_partition(ord, pl.n, rng);
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl)
                 const bool distinct = neg != out && neg != in && out != in;
                 float* rn = item_rec(m, neg); float* ro = item_rec(m, out); float* ri = item_rec(m, in);
                 float wn[V], gnn[V], wo[V], goo[V], wi[V], gii[V], vn[V], vo[V], vi[V];
-                if (distinct) {
+                if (distinct && !atomics) {
                     row_load_cg<D>(rn, lane, wn); row_load_cg<D>(rn + D, lane, gnn);
                     row_load_cg<D>(ro, lane, wo); row_load_cg<D>(ro + D, lane, goo);
                     row_load_cg<D>(ri, lane, wi); row_load_cg<D>(ri + D, lane, gii);
@@ -218,7 +221,33 @@ __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl)
                 }
 #pragma unroll
                 for (int v = 0; v < V; ++v) { gn[v] = g * st[v]; gp[v] = -g * st[v]; }
-                if (distinct) {
+                if (atomics) {
+                    if (distinct) {   // the three visits share one round trip: {ld w, atom G += g^2} x 3, then the reductions
+                        float qn[V], qo[V], qi[V];
+#pragma unroll
+                        for (int v = 0; v < V; ++v) { qn[v] = gn[v] * gn[v]; qo[v] = qn[v]; qi[v] = dx[v] * dx[v]; }
+                        row_load_cg<D>(rn, lane, wn); row_atom_add<D>(rn + D, lane, qn, gnn);
+                        row_load_cg<D>(ro, lane, wo); row_atom_add<D>(ro + D, lane, qo, goo);
+                        row_load_cg<D>(ri, lane, wi); row_atom_add<D>(ri + D, lane, qi, gii);
+                        float dwn[V], dGn[V], dwo[V], dGo[V], dwi[V], dGi[V];
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            adagrad_atomic_elem(wn[v], gnn[v], gn[v], qn[v], o.lr, o.l2, dwn[v], dGn[v]);
+                            adagrad_atomic_elem(wo[v], goo[v], gp[v], qo[v], o.lr, o.l2, dwo[v], dGo[v]);
+                            adagrad_atomic_elem(wi[v], gii[v], dx[v], qi[v], o.lr, o.l2, dwi[v], dGi[v]);
+                        }
+                        row_red_add<D>(rn, lane, dwn); row_red_add<D>(ro, lane, dwo); row_red_add<D>(ri, lane, dwi);
+                        if (o.l2 != 0.0f) { row_red_add<D>(rn + D, lane, dGn); row_red_add<D>(ro + D, lane, dGo); row_red_add<D>(ri + D, lane, dGi); }
+                    } else {
+                        update_row_atomic<D>(rn, lane, gn, o);
+                        update_row_atomic<D>(ro, lane, gp, o);
+                        update_row_atomic<D>(ri, lane, dx, o);
+                    }
+                    if (lane == 0) {
+                        update_bias_atomic(bias_rec(m, neg), g, o);
+                        update_bias_atomic(bias_rec(m, out), -g, o);
+                    }
+                } else if (distinct) {
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
                         if (!o.adam) {
@@ -238,7 +267,7 @@ __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl)
                     update_row<D>(ro, lane, gp, o);
                     update_row<D>(ri, lane, dx, o);
                 }
-                if (lane == 0) {
+                if (lane == 0 && !atomics) {
                     update_bias(bias_rec(m, neg), g, o);
                     update_bias(bias_rec(m, out), -g, o);
                 }
