@@ -20,6 +20,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include <dlfcn.h>
@@ -168,6 +169,52 @@ sbr_status upload_ids_u32(const uint64_t* src, size_t n, uint32_t* dst, cudaStre
 // ============================================================================================================
 // handles
 // ============================================================================================================
+// Transient device buffers of a fit() (id stream mirror, schedule arrays) are recycled: cudaMalloc / cudaFree of a
+// 128 MB buffer cost milliseconds each and cudaFree synchronises the device, which shows up directly in the
+// end-to-end (host CSR in, loss out) rate.  Freed blocks are kept on a bounded free list and handed out again to
+// requests of a similar size; everything here is used on one stream and released only after that stream was synced.
+struct DevPool {
+    std::mutex mu;
+    struct Blk { void* p; size_t bytes; };
+    std::vector<Blk> free_;
+    size_t held = 0;
+    static constexpr size_t kMaxHeld = (size_t)2 << 30; static constexpr size_t kMaxBlocks = 24;
+    cudaError_t alloc(void** out, size_t bytes) {
+        bytes = std::max<size_t>((bytes + 255) & ~(size_t)255, 256);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            size_t best = free_.size();
+            for (size_t i = 0; i < free_.size(); ++i)
+                if (free_[i].bytes >= bytes && free_[i].bytes <= 2 * bytes + (1u << 20) && (best == free_.size() || free_[i].bytes < free_[best].bytes)) best = i;
+            if (best != free_.size()) { *out = free_[best].p; held -= free_[best].bytes; sizes[*out] = free_[best].bytes; free_.erase(free_.begin() + best); return cudaSuccess; }
+        }
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e != cudaSuccess) {   // make room and retry once
+            trim(0);
+            e = cudaMalloc(out, bytes);
+        }
+        if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(mu); sizes[*out] = bytes; }
+        return e;
+    }
+    void release(void* p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = sizes.find(p);
+        if (it == sizes.end()) { cudaFree(p); return; }
+        const size_t bytes = it->second; sizes.erase(it);
+        if (bytes > kMaxHeld / 2) { cudaFree(p); return; }
+        free_.push_back({p, bytes}); held += bytes;
+        while (held > kMaxHeld || free_.size() > kMaxBlocks) { held -= free_.front().bytes; cudaFree(free_.front().p); free_.erase(free_.begin()); }
+    }
+    void trim(size_t keep) {
+        std::lock_guard<std::mutex> lk(mu);
+        while (held > keep && !free_.empty()) { held -= free_.front().bytes; cudaFree(free_.front().p); free_.erase(free_.begin()); }
+    }
+    std::unordered_map<void*, size_t> sizes;
+};
+DevPool g_pool;
+template <typename T> cudaError_t pool_alloc(T** out, size_t bytes) { void* p = nullptr; cudaError_t e = g_pool.alloc(&p, bytes); *out = static_cast<T*>(p); return e; }
+
 struct sbr_compressed {
     size_t num_users = 0, num_items = 0;
     std::vector<uint64_t> user_ptr, item_ids, timestamps;   // owned storage (empty when borrowed)
@@ -180,8 +227,8 @@ struct sbr_compressed {
     mutable uint64_t* d_user_ptr = nullptr;
     mutable size_t upload_bytes = 0;  // bytes moved by the most recent upload (0 if it was already resident)
     ~sbr_compressed() {
-        if (d_item_ids) cudaFree(d_item_ids);
-        if (d_user_ptr) cudaFree(d_user_ptr);
+        g_pool.release(d_item_ids);
+        g_pool.release(d_user_ptr);
     }
 };
 
@@ -235,14 +282,9 @@ struct sbr_fit_plan {
     SyncBuffers* sync = nullptr;
     ~sbr_fit_plan() {
         if (sync) sync_buffers_free(sync);
-        if (d_seq_start) cudaFree(d_seq_start);
-        if (d_seq_len) cudaFree(d_seq_len);
-        if (dev.order) cudaFree(dev.order);
-        if (dev.rng) cudaFree(dev.rng);
-        if (dev.keys) cudaFree(dev.keys);
-        if (dev.step_ctr) cudaFree(dev.step_ctr);
-        if (dev.loss_acc) cudaFree(dev.loss_acc);
-        if (dev.examples) cudaFree(dev.examples);
+        g_pool.release(d_seq_start); g_pool.release(d_seq_len);
+        g_pool.release(dev.order); g_pool.release(dev.rng); g_pool.release(dev.keys);
+        g_pool.release(dev.step_ctr); g_pool.release(dev.loss_acc); g_pool.release(dev.examples);
         if (dev.scratch && !scratch_borrowed) cudaFree(dev.scratch);
         if (scratch_borrowed && model) model->scratch_busy = false;
         for (cudaEvent_t e : {ev0, ev1, evk0, evk1}) if (e) cudaEventDestroy(e);
@@ -258,14 +300,14 @@ sbr_status ensure_uploaded(const sbr_compressed* c, cudaStream_t st) {
     sbr_status s = require_device();
     if (s) return s;
     uint32_t* d = nullptr; uint64_t* dp = nullptr;
-    CU(cudaMalloc(&d, std::max<size_t>(c->nnz_, 1) * sizeof(uint32_t)));
+    CU(pool_alloc(&d, std::max<size_t>(c->nnz_, 1) * sizeof(uint32_t)));
     size_t bytes = 0;
     s = upload_ids_u32(c->ii_, c->nnz_, d, st, c->num_items, &bytes);
-    if (s) { cudaFree(d); return s; }
-    if (cudaMalloc(&dp, (c->num_users + 1) * sizeof(uint64_t)) != cudaSuccess) { cudaFree(d); return cuda_fail(cudaGetLastError(), "cudaMalloc user_ptr"); }
+    if (s) { g_pool.release(d); return s; }
+    if (pool_alloc(&dp, (c->num_users + 1) * sizeof(uint64_t)) != cudaSuccess) { g_pool.release(d); return cuda_fail(cudaGetLastError(), "cudaMalloc user_ptr"); }
     cudaError_t e = cudaMemcpyAsync(dp, c->up_, (c->num_users + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { cudaFree(d); cudaFree(dp); return cuda_fail(e, "upload user_ptr"); }
+    if (e != cudaSuccess) { g_pool.release(d); g_pool.release(dp); return cuda_fail(e, "upload user_ptr"); }
     bytes += (c->num_users + 1) * sizeof(uint64_t);
     c->d_item_ids = d; c->d_user_ptr = dp; c->upload_bytes = bytes;
     return SBR_OK;
@@ -759,14 +801,14 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     size_t h2d = c->upload_bytes;
     PlanDev& d = pl->dev;
     d.item_ids = c->d_item_ids;
-    CUP(cudaMalloc(&pl->d_seq_start, nsub * sizeof(uint64_t)));
-    CUP(cudaMalloc(&pl->d_seq_len, nsub * sizeof(uint32_t)));
-    CUP(cudaMalloc(&d.order, P * n * sizeof(uint32_t)));
-    CUP(cudaMalloc(&d.rng, P * sizeof(XorShift)));
-    CUP(cudaMalloc(&d.keys, P * sizeof(uint64_t)));
-    CUP(cudaMalloc(&d.step_ctr, P * sizeof(uint64_t)));
-    CUP(cudaMalloc(&d.loss_acc, P * sizeof(float)));
-    CUP(cudaMalloc(&d.examples, P * sizeof(unsigned long long)));
+    CUP(pool_alloc(&pl->d_seq_start, nsub * sizeof(uint64_t)));
+    CUP(pool_alloc(&pl->d_seq_len, nsub * sizeof(uint32_t)));
+    CUP(pool_alloc(&d.order, P * n * sizeof(uint32_t)));
+    CUP(pool_alloc(&d.rng, P * sizeof(XorShift)));
+    CUP(pool_alloc(&d.keys, P * sizeof(uint64_t)));
+    CUP(pool_alloc(&d.step_ctr, P * sizeof(uint64_t)));
+    CUP(pool_alloc(&d.loss_acc, P * sizeof(float)));
+    CUP(pool_alloc(&d.examples, P * sizeof(unsigned long long)));
     d.scratch_stride = train_scratch_floats_per_warp(m->dev);
     {
         const size_t need = P * d.scratch_stride * sizeof(float);
