@@ -103,9 +103,10 @@ template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.as
 // (core-matrix order: lane-per-row accesses and the cooperative 8-rows-per-chunk accesses are both conflict-free).
 struct Slice { uint8_t* p; uint32_t gs; };
 
-struct Table { float* e0; uint32_t stride; bool flat; };   // item_rec() with the unsharded case resolved once
-__device__ __forceinline__ float* trec(const ModelDev& m, const Table& tb, uint32_t id) {
-    return tb.flat ? tb.e0 + (size_t)id * tb.stride : item_rec(m, id);
+// item_rec() with the shard base pointers in shared memory: AND, SHR, LDS.64, IMAD.WIDE for any shard count
+struct Table { float* const* es; uint32_t stride, gmask; int gshift; };
+__device__ __forceinline__ float* trec(const ModelDev&, const Table& tb, uint32_t id) {
+    return tb.es[id & tb.gmask] + (size_t)(id >> tb.gshift) * tb.stride;
 }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
@@ -159,7 +160,9 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
     const size_t nd = m.ndense;
     const bool coupled = m.variant == 1;
     const int T = m.T;
-    Table tb; tb.e0 = m.Es[0]; tb.stride = (uint32_t)(m.S * m.D); tb.flat = m.gmask == 0;
+    float** es_s = reinterpret_cast<float**>(smem + OFF_MISC + 64);         // [8] shard base pointers of the item table
+    if (tid < 8) es_s[tid] = m.Es[tid];
+    Table tb; tb.es = es_s; tb.stride = (uint32_t)(m.S * m.D); tb.gmask = m.gmask; tb.gshift = m.gshift;
 
     auto tile_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(tile + 1), "n"(TT) : "memory"); };
     auto quad_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(3 + tile * 4 + q), "n"(32 * DS) : "memory"); };
@@ -353,6 +356,7 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
     tc_fence_after_sync();
     const uint32_t tbase = *tmem_ptr + (uint32_t)tile * 256u + ((uint32_t)(q * 32) << 16);   // this thread's TMEM lane, tile's columns
     const uint32_t tcol0 = *tmem_ptr + (uint32_t)tile * 256u;                                 // for the MMA issuer
+    const uint32_t tcs = tbase + 208u + (uint32_t)(part * DPT);                               // this thread's cell-state columns
     const uint32_t zt_a = smem_u32(Zt), db_a = smem_u32(Db), zb_a = smem_u32(Zb), wt_a = smem_u32(Wt), wb_a = smem_u32(Wb);
     constexpr uint32_t IDESC_G1 = make_idesc_tf32(128, 128, 0, 0);
     constexpr uint32_t IDESC_G2 = make_idesc_bf16(128, 64, 0, 0);
@@ -391,9 +395,17 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
             const int Tmax = tmax_s[tile];
 
             // =========================== forward ===========================
-            float h[DPT], c[DPT];
+            // The cell state (forward) and the cell-gradient recurrence (backward) are touched once per timestep, inside
+            // the gate / delta loops: they live in 32 spare TMEM columns of the tile (208..239), not in registers.
+            float h[DPT];
 #pragma unroll
-            for (int d = 0; d < DPT; ++d) { h[d] = 0.0f; c[d] = 0.0f; }
+            for (int d = 0; d < DPT; ++d) h[d] = 0.0f;
+            {
+                const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int b = 0; b < NB8; ++b) tmem_st8(tcs + b * 8, z8);
+                tmem_st_wait();
+            }
             float loss_seq = 0.0f;
             // ids[t+1], ids[t+2] travel in registers, loaded one step ahead of their use (ids has Tn + 1 entries)
             uint32_t idB = 0, idC = 0;
@@ -470,6 +482,7 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                 for (int b = 0; b < NB8; ++b) {
                     const int gb = gb0 + b;
                     float pf[8], pi[8], pg[8], po[8], pc[8], ptc[8];
+                    tmem_ld8(tcs + b * 8, pc);   // c_{t-1}
                     tmem_ld8x4(tbase + gb * 8, tbase + 32 + gb * 8, tbase + 64 + gb * 8, tbase + 96 + gb * 8, pf, pi, pg, po);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -478,12 +491,13 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                         const float ig = coupled ? 1.0f - f : sigm(pi[j] + bias_s[32 + dg_]);
                         const float gg = tnh(pg[j] + bias_s[64 + dg_]);
                         const float og = sigm(po[j] + bias_s[96 + dg_]);
-                        const float cn = f * c[d] + ig * gg;
+                        const float cn = f * pc[j] + ig * gg;
                         const float tcn = tnh(cn);
                         const float hn = og * tcn;
-                        if (act) { c[d] = cn; h[d] = hn; } else h[d] = 0.0f;
+                        h[d] = act ? hn : 0.0f;
                         pf[j] = f; pi[j] = ig; pg[j] = gg; po[j] = og; pc[j] = cn; ptc[j] = tcn;
                     }
+                    tmem_st8(tcs + b * 8, pc);   // (finished sequences carry garbage from here on: never read again as a live value)
                     if (act) {
                         *sb8(t, AF, gb) = pack_bf16x8(pf); *sb8(t, AI, gb) = pack_bf16x8(pi);
                         *sb8(t, AG, gb) = pack_bf16x8(pg); *sb8(t, AO, gb) = pack_bf16x8(po);
@@ -494,6 +508,7 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                         *sf4(t, 2 * gb + 1) = make_float4(h8[4], h8[5], h8[6], h8[7]);
                     }
                 }
+                tmem_st_wait();
                 tc_fence_before_sync();  // TMEM reads ordered before the next MMA (issued after the next tile barrier)
                 // scoring + negative sampling (sequence_model.rs:47-68, lstm.rs:300-320)
                 cp_wait<1>();            // G1 (target, candidates 0 and 1) has landed; G2 may still fly
@@ -583,9 +598,12 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
             // =========================== backward ===========================
             // dz of timestep t+1 (dh_t in TMEM columns 0..31, dx_{t+1} in 32..63) is consumed straight from TMEM inside
             // timestep t's delta loop -- nothing but the cell-gradient recurrence lives in registers across timesteps.
-            float dc_rec[DPT];
+            {
+                const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int d = 0; d < DPT; ++d) dc_rec[d] = 0.0f;
+                for (int b = 0; b < NB8; ++b) tmem_st8(tcs + b * 8, z8);   // dc_t recurrence starts at 0
+                tmem_st_wait();
+            }
             float g_c = 0.0f; uint32_t neg_c = 0, out_c = 0;
             ActB cur;
             {
@@ -611,7 +629,8 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                     for (int b = 0; b < NB8; ++b) {
                         const int gb = gb0 + b;
                         if (b > 0) load_act(cur, t, gb, act);   // (no double buffering: 128 registers per thread)
-                        float dhv[8];
+                        float dhv[8], dcv[8];
+                        tmem_ld8(tcs + b * 8, dcv);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) dhv[e] = 0.0f;
                         if (prev_valid) {   // dh_t and dx_{t+1}
@@ -634,16 +653,16 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                             float rdf[2], rdi[2], rdg[2], rdo[2];
 #pragma unroll
                             for (int k = 0; k < 2; ++k) {
-                                const int e = 2 * pr + k, d = b * 8 + e;
+                                const int e = 2 * pr + k;
                                 const float f_ = k ? bf_hi(uf) : bf_lo(uf), i_ = k ? bf_hi(ui) : bf_lo(ui), g_ = k ? bf_hi(ug) : bf_lo(ug);
                                 const float o_ = k ? bf_hi(uo) : bf_lo(uo), q_ = k ? bf_hi(uq) : bf_lo(uq);
                                 const float cp_ = k ? bf_hi(ucp) : bf_lo(ucp), tcv = k ? bf_hi(utc) : bf_lo(utc);
                                 const float dh = dhv[e] + q_;
                                 const float d_o = dh * tcv;
-                                const float dc = dc_rec[d] + dh * o_ * (1.0f - tcv * tcv);
+                                const float dc = dcv[e] + dh * o_ * (1.0f - tcv * tcv);
                                 float d_f = dc * cp_, d_i = dc * g_;
                                 const float d_g = dc * i_;
-                                dc_rec[d] = act ? dc * f_ : 0.0f;
+                                dcv[e] = act ? dc * f_ : 0.0f;
                                 if (coupled) { d_f -= d_i; d_i = 0.0f; }
                                 rdf[k] = d_f * f_ * (1.0f - f_);
                                 rdi[k] = coupled ? 0.0f : d_i * i_ * (1.0f - i_);
@@ -657,7 +676,9 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                         *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 4 + gb, 16)) = make_uint4(wdi[0], wdi[1], wdi[2], wdi[3]);
                         *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 8 + gb, 16)) = make_uint4(wdg[0], wdg[1], wdg[2], wdg[3]);
                         *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 12 + gb, 16)) = make_uint4(wdo[0], wdo[1], wdo[2], wdo[3]);
+                        tmem_st8(tcs + b * 8, dcv);
                     }
+                    tmem_st_wait();
                     cp_wait<0>();             // Z_t rows have landed
                     fence_async_smem();
                     tc_fence_before_sync();   // also orders this thread's TMEM reads of dz_{t+1} before the MMA that overwrites them

@@ -1,7 +1,8 @@
 """Tensor-core LSTM kernel (tcgen05 tiles, kernels_lstm_tc.cu) against the CPU oracle.
 
-The tile kernel is the throughput path (num_threads a multiple of 128): tf32 forward products, bf16 backward products,
-fp32 accumulation, MUFU exp/rcp/rsqrt.  Stated tolerance of this mode: one round of 128*NT sequences from identical
+The tile kernels are the throughput path (num_threads a multiple of 128): tf32 forward products, bf16 backward products
+and bf16 copies of the saved activations, fp32 accumulation, MUFU ex2/rcp/rsqrt; Hogwild Adagrad visits through L2
+atomics (atom.add on the accumulator, red.add on the weights).  Stated tolerance of this mode: one round of 128*NT sequences from identical
 parameters reproduces the oracle's parameters to |diff| <= 4e-4 at lr 0.05 (updates themselves are O(1e-2)), i.e.
 gradients to ~1 % -- the bf16 operand rounding.  Many partitions race (Hogwild), so the element-wise check uses a
 construction where the races cannot matter: every partition trains exactly one sequence over its own items, all
@@ -26,8 +27,16 @@ def _adagrad(w, G, g, lr, l2):
     return w.astype(np.float32), G.astype(np.float32)
 
 
-@pytest.mark.parametrize("P,variant", [(128, "normal"), (256, "normal"), (256, "coupled")])
-def test_one_round_matches_oracle_gradients(pkg, oracle, P, variant):
+# every generation of the tile kernel stays under the same parity gate (SBR_LSTM_TC, kernels_train.cu:launch_train):
+# "3" = default (2 threads per sequence, L2-atomic Adagrad), "34" = 4 threads per sequence, "2" = thread per sequence
+# with the prefetch pipeline, "1" = the first tile kernel
+GENERATIONS = [("3", 128, "normal"), ("3", 256, "normal"), ("3", 256, "coupled"), ("34", 256, "normal"), ("2", 256, "normal"),
+               ("2", 128, "coupled"), ("1", 256, "normal")]
+
+
+@pytest.mark.parametrize("gen,P,variant", GENERATIONS)
+def test_one_round_matches_oracle_gradients(pkg, oracle, monkeypatch, gen, P, variant):
+    monkeypatch.setenv("SBR_LSTM_TC", gen)
     N, T, D, lr, l2 = 60000, 8, 32, 0.05, 1e-3
     ptr = (np.arange(P + 1) * T).astype(np.uint64)
     ids = (1000 + np.arange(P * T)).astype(np.uint64)          # user u owns items 1000+8u .. 1000+8u+7
