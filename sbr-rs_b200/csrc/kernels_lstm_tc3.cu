@@ -242,89 +242,75 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
     // The sparse visits of one backward timestep, this warp's chunks of the 32 rows (flags as in kernels_lstm_tc2.cu):
     //   bit 0: E[neg] += step(+g h)      bit 1: visit E[out]: [bit 2: step(dx_{t+1})] [bit 3: step(+g h)] [bit 4: step(-g h)]
     const bool noatom = (pl.dbg_flags & 8) != 0 || m.hbm_resident != 0;   // hot rows only exist on L2-resident tables
-    auto coop_visits = [&](uint32_t neg, uint32_t out, uint32_t fl, const Slice& gh, const Slice& dx, const OptCfg& o) {
+    // A pass covers GPP row groups (NGI / GPP passes per timestep).  It is split in two so that the round trip of the
+    // first pass -- {ld w, atom G} or {ld w, ld G} -- flies while the tile meets at its barrier and the MMAs are issued.
+    constexpr int GPP = NGI >= 2 ? 2 : 1;   // row groups per pass: 4 row visits (w, s each) in flight
+    struct VisitState { float* rn[GPP]; float* ro[GPP]; uint32_t f[GPP]; uint32_t off[GPP]; float4 wn[GPP], sn[GPP], wo[GPP], so[GPP]; };
+    auto atom_amount_out = [&](uint32_t f, const float4& s4, const Slice& dx, uint32_t off) -> float4 {   // what the atom adds to G[out]
+        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f & 4u) t4 = sq4(*reinterpret_cast<const float4*>(dx.p + off));
+        if (f & 8u) t4 = add4(t4, s4);
+        if (f & 16u) t4 = add4(t4, s4);
+        return t4;
+    };
+    auto visit_issue = [&](int pass, VisitState& V, uint32_t neg, uint32_t out, uint32_t fl, const Slice& gh, const Slice& dx, const OptCfg& o) {
         const int rl = lane % RPI, ch = lane / RPI;
-        constexpr int GPP = NGI >= 2 ? 2 : 1;   // row groups per pass: 4 row visits (w, s each) in flight
+        const bool atomics = !o.adam && !noatom;
 #pragma unroll
-        for (int pass = 0; pass < NGI / GPP; ++pass) {
-            float* rn[GPP]; float* ro[GPP]; uint32_t f[GPP]; uint32_t off[GPP];
-            float4 wn[GPP], sn[GPP], wo[GPP], so[GPP];
+        for (int gg = 0; gg < GPP; ++gg) {
+            const int row = (pass * GPP + gg) * RPI + rl;
+            const uint32_t idn = __shfl_sync(kFull, neg, row), ido = __shfl_sync(kFull, out, row);
+            V.f[gg] = __shfl_sync(kFull, fl, row);
+            V.rn[gg] = trec(m, tb, idn) + part * DPT + ch * 4; V.ro[gg] = trec(m, tb, ido) + part * DPT + ch * 4;
+            V.off[gg] = (uint32_t)(row >> 3) * GS + (uint32_t)ch * 128u + (uint32_t)(row & 7) * 16u;
+        }
 #pragma unroll
-            for (int gg = 0; gg < GPP; ++gg) {
-                const int row = (pass * GPP + gg) * RPI + rl;
-                const uint32_t idn = __shfl_sync(kFull, neg, row), ido = __shfl_sync(kFull, out, row);
-                f[gg] = __shfl_sync(kFull, fl, row);
-                rn[gg] = trec(m, tb, idn) + part * DPT + ch * 4; ro[gg] = trec(m, tb, ido) + part * DPT + ch * 4;
-                off[gg] = (uint32_t)(row >> 3) * GS + (uint32_t)ch * 128u + (uint32_t)(row & 7) * 16u;
+        for (int gg = 0; gg < GPP; ++gg) {
+            if (atomics) {
+                const float4 s4 = sq4(*reinterpret_cast<const float4*>(gh.p + V.off[gg]));
+                if (V.f[gg] & 1u) { V.wn[gg] = __ldcg(reinterpret_cast<const float4*>(V.rn[gg])); V.sn[gg] = atom_add4(V.rn[gg] + kD, s4); }
+                if (V.f[gg] & 2u) { V.wo[gg] = __ldcg(reinterpret_cast<const float4*>(V.ro[gg])); V.so[gg] = atom_add4(V.ro[gg] + kD, atom_amount_out(V.f[gg], s4, dx, V.off[gg])); }
+            } else {
+                if (V.f[gg] & 1u) { V.wn[gg] = __ldcg(reinterpret_cast<const float4*>(V.rn[gg])); V.sn[gg] = __ldcg(reinterpret_cast<const float4*>(V.rn[gg] + kD)); }
+                if (V.f[gg] & 2u) { V.wo[gg] = __ldcg(reinterpret_cast<const float4*>(V.ro[gg])); V.so[gg] = __ldcg(reinterpret_cast<const float4*>(V.ro[gg] + kD)); }
             }
-            if (!o.adam && !noatom) {
-                float4 gn[GPP], go[GPP];   // what the atom added up front: sum of squared raw gradients
+        }
+    };
+    // flags: bit 0: E[neg] += step(+g h)      bit 1: visit E[out]: [bit 2: step(dx_{t+1})] [bit 3: step(+g h)] [bit 4: step(-g h)]
+    auto visit_finish = [&](VisitState& V, const Slice& gh, const Slice& dx, const OptCfg& o) {
+        const bool atomics = !o.adam && !noatom;
 #pragma unroll
-                for (int gg = 0; gg < GPP; ++gg) {
-                    const float4 s4 = sq4(*reinterpret_cast<const float4*>(gh.p + off[gg]));
-                    if (f[gg] & 1u) {
-                        gn[gg] = s4;
-                        wn[gg] = __ldcg(reinterpret_cast<const float4*>(rn[gg]));
-                        sn[gg] = atom_add4(rn[gg] + kD, s4);
-                    }
-                    if (f[gg] & 2u) {
-                        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (f[gg] & 4u) t4 = sq4(*reinterpret_cast<const float4*>(dx.p + off[gg]));
-                        if (f[gg] & 8u) t4 = add4(t4, s4);
-                        if (f[gg] & 16u) t4 = add4(t4, s4);
-                        go[gg] = t4;
-                        wo[gg] = __ldcg(reinterpret_cast<const float4*>(ro[gg]));
-                        so[gg] = atom_add4(ro[gg] + kD, t4);
-                    }
+        for (int gg = 0; gg < GPP; ++gg) {
+            const float4 g4 = *reinterpret_cast<const float4*>(gh.p + V.off[gg]);
+            if (V.f[gg] & 1u) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (o.adam) v = __ldcg(reinterpret_cast<const float4*>(V.rn[gg] + 2 * kD));
+                const float4 w0 = V.wn[gg], G0 = V.sn[gg];
+                apply4(V.wn[gg], V.sn[gg], v, g4, 1.0f, o);
+                if (atomics) {
+                    red_add4(V.rn[gg], sub4(V.wn[gg], w0));
+                    if (o.l2 != 0.0f) red_add4(V.rn[gg] + kD, sub4(sub4(V.sn[gg], G0), sq4(g4)));
+                } else {
+                    __stcg(reinterpret_cast<float4*>(V.rn[gg]), V.wn[gg]); __stcg(reinterpret_cast<float4*>(V.rn[gg] + kD), V.sn[gg]);
+                    if (o.adam) __stcg(reinterpret_cast<float4*>(V.rn[gg] + 2 * kD), v);
                 }
-#pragma unroll
-                for (int gg = 0; gg < GPP; ++gg) {
-                    const float4 g4 = *reinterpret_cast<const float4*>(gh.p + off[gg]);
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (f[gg] & 1u) {
-                        const float4 w0 = wn[gg], G0 = sn[gg];
-                        apply4(wn[gg], sn[gg], v, g4, 1.0f, o);
-                        red_add4(rn[gg], sub4(wn[gg], w0));
-                        if (o.l2 != 0.0f) red_add4(rn[gg] + kD, sub4(sub4(sn[gg], G0), gn[gg]));
-                    }
-                    if (f[gg] & 2u) {
-                        const float4 w0 = wo[gg], G0 = so[gg];
-                        if (f[gg] & 4u) { const float4 d4 = *reinterpret_cast<const float4*>(dx.p + off[gg]); apply4(wo[gg], so[gg], v, d4, 1.0f, o); }
-                        if (f[gg] & 8u) apply4(wo[gg], so[gg], v, g4, 1.0f, o);
-                        if (f[gg] & 16u) apply4(wo[gg], so[gg], v, g4, -1.0f, o);
-                        red_add4(ro[gg], sub4(wo[gg], w0));
-                        if (o.l2 != 0.0f) red_add4(ro[gg] + kD, sub4(sub4(so[gg], G0), go[gg]));
-                    }
-                }
-                continue;
             }
-#pragma unroll
-            for (int gg = 0; gg < GPP; ++gg) {
-                if (f[gg] & 1u) { wn[gg] = __ldcg(reinterpret_cast<const float4*>(rn[gg])); sn[gg] = __ldcg(reinterpret_cast<const float4*>(rn[gg] + kD)); }
-                if (f[gg] & 2u) { wo[gg] = __ldcg(reinterpret_cast<const float4*>(ro[gg])); so[gg] = __ldcg(reinterpret_cast<const float4*>(ro[gg] + kD)); }
-            }
-#pragma unroll
-            for (int gg = 0; gg < GPP; ++gg) {
-                const float4 g4 = *reinterpret_cast<const float4*>(gh.p + off[gg]);
-                if (f[gg] & 1u) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (o.adam) v = __ldcg(reinterpret_cast<const float4*>(rn[gg] + 2 * kD));
-                    apply4(wn[gg], sn[gg], v, g4, 1.0f, o);
-                    __stcg(reinterpret_cast<float4*>(rn[gg]), wn[gg]); __stcg(reinterpret_cast<float4*>(rn[gg] + kD), sn[gg]);
-                    if (o.adam) __stcg(reinterpret_cast<float4*>(rn[gg] + 2 * kD), v);
-                }
-                if (f[gg] & 2u) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (o.adam) v = __ldcg(reinterpret_cast<const float4*>(ro[gg] + 2 * kD));
-                    if (f[gg] & 4u) { const float4 d4 = *reinterpret_cast<const float4*>(dx.p + off[gg]); apply4(wo[gg], so[gg], v, d4, 1.0f, o); }
-                    if (f[gg] & 8u) apply4(wo[gg], so[gg], v, g4, 1.0f, o);
-                    if (f[gg] & 16u) apply4(wo[gg], so[gg], v, g4, -1.0f, o);
-                    __stcg(reinterpret_cast<float4*>(ro[gg]), wo[gg]); __stcg(reinterpret_cast<float4*>(ro[gg] + kD), so[gg]);
-                    if (o.adam) __stcg(reinterpret_cast<float4*>(ro[gg] + 2 * kD), v);
+            if (V.f[gg] & 2u) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (o.adam) v = __ldcg(reinterpret_cast<const float4*>(V.ro[gg] + 2 * kD));
+                const float4 w0 = V.wo[gg], G0 = V.so[gg];
+                if (V.f[gg] & 4u) { const float4 d4 = *reinterpret_cast<const float4*>(dx.p + V.off[gg]); apply4(V.wo[gg], V.so[gg], v, d4, 1.0f, o); }
+                if (V.f[gg] & 8u) apply4(V.wo[gg], V.so[gg], v, g4, 1.0f, o);
+                if (V.f[gg] & 16u) apply4(V.wo[gg], V.so[gg], v, g4, -1.0f, o);
+                if (atomics) {
+                    red_add4(V.ro[gg], sub4(V.wo[gg], w0));
+                    if (o.l2 != 0.0f) red_add4(V.ro[gg] + kD, sub4(sub4(V.so[gg], G0), atom_amount_out(V.f[gg], sq4(g4), dx, V.off[gg])));
+                } else {
+                    __stcg(reinterpret_cast<float4*>(V.ro[gg]), V.wo[gg]); __stcg(reinterpret_cast<float4*>(V.ro[gg] + kD), V.so[gg]);
+                    if (o.adam) __stcg(reinterpret_cast<float4*>(V.ro[gg] + 2 * kD), v);
                 }
             }
         }
-        __syncwarp();
     };
 
     // ---- one-time setup ----
@@ -622,6 +608,10 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                 if (actn) { g_n = __ldcg(G_ + (size_t)(t - 1) * gstride); neg_n = __ldcg(NEG + (size_t)(t - 1) * gstride); out_n = __ldg(ids + t); }
                 else if (t == 0 && Tn > 0) out_n = __ldg(ids);   // out_{-1} = ids[0] = in_0
                 if (t >= 1) prefetch_step(t - 1);
+                const bool triple = act && neg == out;
+                const bool has_dx = t + 1 < Tn;   // a deferred E[in_{t+1}] entry exists (t + 1 >= 0 always)
+                const uint32_t fl = (act && !triple ? 1u : 0u) | ((act || has_dx) ? 2u : 0u) | (has_dx ? 4u : 0u) | (triple ? 8u : 0u) | (act ? 16u : 0u);
+                VisitState VS;
                 if (prev_valid) { mbar_wait(mbar + tile, phase); phase ^= 1; tc_fence_after_sync(); }
                 if (t >= 0) {
                     stage_z_async(t, act);   // the previous MMA is done with the Z tile
@@ -679,6 +669,8 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                         tmem_st8(tcs + b * 8, dcv);
                     }
                     tmem_st_wait();
+                    __syncwarp();             // the g h_t and dx_{t+1} slices are complete
+                    visit_issue(0, VS, neg, out, fl, SZ0, SZ1, o);   // first pass of the visits flies across the barrier and the MMA issue
                     cp_wait<0>();             // Z_t rows have landed
                     fence_async_smem();
                     tc_fence_before_sync();   // also orders this thread's TMEM reads of dz_{t+1} before the MMA that overwrites them
@@ -706,13 +698,11 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                         slice_st(SZ1, 2 * b + 1, make_float4(__uint_as_float(rb[4]), __uint_as_float(rb[5]), __uint_as_float(rb[6]), __uint_as_float(rb[7])));
                     }
                     tc_fence_before_sync();
+                    __syncwarp();            // the dx_0 slice is complete
+                    visit_issue(0, VS, neg, out, fl, SZ0, SZ1, o);
                 }
-                __syncwarp();            // the g h_t and dx_{t+1} slices are complete
                 // ---- sparse visits of this timestep (overlap the MMAs): E[neg_t]; E[out_t] with the deferred E[in_{t+1}] ----
                 {
-                    const bool triple = act && neg == out;
-                    const bool has_dx = t + 1 < Tn;   // a deferred E[in_{t+1}] entry exists (t + 1 >= 0 always)
-                    const uint32_t fl = (act && !triple ? 1u : 0u) | ((act || has_dx) ? 2u : 0u) | (has_dx ? 4u : 0u) | (triple ? 8u : 0u) | (act ? 16u : 0u);
                     float4* rn = bias_rec(m, neg); float4* ro = bias_rec(m, out);
                     float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
                     const bool bv = act && lead;
@@ -724,7 +714,10 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                             if (neg != out) { bb.x = __ldcg(fo_); bb.y = atomicAdd(fo_ + 1, g * g); }
                         } else { ba = __ldcg(rn); if (neg != out) bb = __ldcg(ro); }
                     }
-                    coop_visits(neg, out, fl, SZ0, SZ1, o);
+                    visit_finish(VS, SZ0, SZ1, o);
+#pragma unroll
+                    for (int pass = 1; pass < NGI / GPP; ++pass) { visit_issue(pass, VS, neg, out, fl, SZ0, SZ1, o); visit_finish(VS, SZ0, SZ1, o); }
+                    __syncwarp();
                     if (bv) {   // b[neg] += step(+g), b[out] += step(-g)
                         const float4 a0 = ba, b0 = bb;
                         if (neg != out) {
