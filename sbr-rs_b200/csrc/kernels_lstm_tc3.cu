@@ -103,9 +103,11 @@ template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.as
 // (core-matrix order: lane-per-row accesses and the cooperative 8-rows-per-chunk accesses are both conflict-free).
 struct Slice { uint8_t* p; uint32_t gs; };
 
-// item_rec() with the shard base pointers in shared memory: AND, SHR, LDS.64, IMAD.WIDE for any shard count
-struct Table { float* const* es; uint32_t stride, gmask; int gshift; };
-__device__ __forceinline__ float* trec(const ModelDev&, const Table& tb, uint32_t id) {
+// item_rec(): one multiply-add on an unsharded table (FLAT); shard base pointers from shared memory otherwise
+struct Table { float* e0; float* const* es; uint32_t stride, gmask; int gshift; };
+template <bool FLAT>
+__device__ __forceinline__ float* trec(const Table& tb, uint32_t id) {
+    if (FLAT) return tb.e0 + (size_t)id * tb.stride;
     return tb.es[id & tb.gmask] + (size_t)(id >> tb.gshift) * tb.stride;
 }
 
@@ -122,7 +124,7 @@ struct ActB {
     float4 h0, h1;                  // h_t fp32
 };
 
-template <int NT, int DS>
+template <int NT, int DS, bool FLAT>
 __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelDev m, PlanDev pl) {
     constexpr int DPT = 32 / DS;       // hidden units per thread
     constexpr int NCH = DPT / 4;       // 16-byte fp32 chunks of a row per thread
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
     const int T = m.T;
     float** es_s = reinterpret_cast<float**>(smem + OFF_MISC + 64);         // [8] shard base pointers of the item table
     if (tid < 8) es_s[tid] = m.Es[tid];
-    Table tb; tb.es = es_s; tb.stride = (uint32_t)(m.S * m.D); tb.gmask = m.gmask; tb.gshift = m.gshift;
+    Table tb; tb.e0 = m.Es[0]; tb.es = es_s; tb.stride = (uint32_t)(m.S * m.D); tb.gmask = m.gmask; tb.gshift = m.gshift;
 
     auto tile_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(tile + 1), "n"(TT) : "memory"); };
     auto quad_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(3 + tile * 4 + q), "n"(32 * DS) : "memory"); };
@@ -187,11 +189,14 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
     auto gather_async = [&](uint32_t my_id, const Slice& s) {
         const int rl = lane % RPI, ch = lane / RPI;
         const uint32_t base = smem_u32(s.p) + ch * 128;
+        const float* src[NGI];
+#pragma unroll
+        for (int i = 0; i < NGI; ++i)   // all addresses first: the copies below are compiler barriers
+            src[i] = trec<FLAT>(tb, __shfl_sync(kFull, my_id, i * RPI + rl)) + part * DPT + ch * 4;
 #pragma unroll
         for (int i = 0; i < NGI; ++i) {
             const int row = i * RPI + rl;
-            const uint32_t id = __shfl_sync(kFull, my_id, row);
-            cp_async16(base + (row >> 3) * s.gs + (row & 7) * 16, trec(m, tb, id) + part * DPT + ch * 4);
+            cp_async16(base + (row >> 3) * s.gs + (row & 7) * 16, src[i]);
         }
     };
 
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
             const int row = (pass * GPP + gg) * RPI + rl;
             const uint32_t idn = __shfl_sync(kFull, neg, row), ido = __shfl_sync(kFull, out, row);
             V.f[gg] = __shfl_sync(kFull, fl, row);
-            V.rn[gg] = trec(m, tb, idn) + part * DPT + ch * 4; V.ro[gg] = trec(m, tb, ido) + part * DPT + ch * 4;
+            V.rn[gg] = trec<FLAT>(tb, idn) + part * DPT + ch * 4; V.ro[gg] = trec<FLAT>(tb, ido) + part * DPT + ch * 4;
             V.off[gg] = (uint32_t)(row >> 3) * GS + (uint32_t)ch * 128u + (uint32_t)(row & 7) * 16u;
         }
 #pragma unroll
@@ -282,6 +287,7 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
 #pragma unroll
         for (int gg = 0; gg < GPP; ++gg) {
             const float4 g4 = *reinterpret_cast<const float4*>(gh.p + V.off[gg]);
+            const float4 d4 = *reinterpret_cast<const float4*>(dx.p + V.off[gg]);
             if (V.f[gg] & 1u) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (o.adam) v = __ldcg(reinterpret_cast<const float4*>(V.rn[gg] + 2 * kD));
@@ -299,12 +305,19 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (o.adam) v = __ldcg(reinterpret_cast<const float4*>(V.ro[gg] + 2 * kD));
                 const float4 w0 = V.wo[gg], G0 = V.so[gg];
-                if (V.f[gg] & 4u) { const float4 d4 = *reinterpret_cast<const float4*>(dx.p + V.off[gg]); apply4(V.wo[gg], V.so[gg], v, d4, 1.0f, o); }
+                if (V.f[gg] & 4u) apply4(V.wo[gg], V.so[gg], v, d4, 1.0f, o);
                 if (V.f[gg] & 8u) apply4(V.wo[gg], V.so[gg], v, g4, 1.0f, o);
                 if (V.f[gg] & 16u) apply4(V.wo[gg], V.so[gg], v, g4, -1.0f, o);
                 if (atomics) {
                     red_add4(V.ro[gg], sub4(V.wo[gg], w0));
-                    if (o.l2 != 0.0f) red_add4(V.ro[gg] + kD, sub4(sub4(V.so[gg], G0), atom_amount_out(V.f[gg], sq4(g4), dx, V.off[gg])));
+                    if (o.l2 != 0.0f) {
+                        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 q4 = sq4(g4);
+                        if (V.f[gg] & 4u) t4 = sq4(d4);
+                        if (V.f[gg] & 8u) t4 = add4(t4, q4);
+                        if (V.f[gg] & 16u) t4 = add4(t4, q4);
+                        red_add4(V.ro[gg] + kD, sub4(sub4(V.so[gg], G0), t4));
+                    }
                 } else {
                     __stcg(reinterpret_cast<float4*>(V.ro[gg]), V.wo[gg]); __stcg(reinterpret_cast<float4*>(V.ro[gg] + kD), V.so[gg]);
                     if (o.adam) __stcg(reinterpret_cast<float4*>(V.ro[gg] + 2 * kD), v);
@@ -809,14 +822,14 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
     if (tid < 32) tmem_dealloc<(NT == 1 ? 256 : 512)>(*tmem_ptr);
 }
 
-template <int NT, int DS>
+template <int NT, int DS, bool FLAT>
 cudaError_t launch_one(const ModelDev& m, const PlanDev& p, cudaStream_t st) {
     const size_t smem = OFF_TILES + (size_t)NT * TILE_BYTES + (size_t)NT * 4 * XS_BYTES_PER_QUAD;
     const int seq_per_cta = 128 * NT;
     dim3 grid((p.P + seq_per_cta - 1) / seq_per_cta);
-    cudaError_t e = cudaFuncSetAttribute(lstm_tc3_train_kernel<NT, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(lstm_tc3_train_kernel<NT, DS, FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    lstm_tc3_train_kernel<NT, DS><<<grid, seq_per_cta * DS, smem, st>>>(m, p);
+    lstm_tc3_train_kernel<NT, DS, FLAT><<<grid, seq_per_cta * DS, smem, st>>>(m, p);
     return cudaGetLastError();
 }
 
@@ -825,8 +838,13 @@ cudaError_t launch_one(const ModelDev& m, const PlanDev& p, cudaStream_t st) {
 }  // namespace
 
 cudaError_t launch_lstm_tc3(const ModelDev& m, const PlanDev& p, int nt, int ds, cudaStream_t st) {
-    if (ds == 4) return nt == 2 ? launch_one<2, 4>(m, p, st) : launch_one<1, 4>(m, p, st);
-    return nt == 2 ? launch_one<2, 2>(m, p, st) : launch_one<1, 2>(m, p, st);
+    const bool flat = m.gmask == 0;
+    if (ds == 4) {   // experiment only: 64 registers per thread spill
+        if (nt == 2) return flat ? launch_one<2, 4, true>(m, p, st) : launch_one<2, 4, false>(m, p, st);
+        return flat ? launch_one<1, 4, true>(m, p, st) : launch_one<1, 4, false>(m, p, st);
+    }
+    if (nt == 2) return flat ? launch_one<2, 2, true>(m, p, st) : launch_one<2, 2, false>(m, p, st);
+    return flat ? launch_one<1, 2, true>(m, p, st) : launch_one<1, 2, false>(m, p, st);
 }
 
 }  // namespace sbr
