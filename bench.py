@@ -249,7 +249,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_kind": peak_kind, "kernel": "lstm_tc3_train_kernel<2,2> (tcgen05 tile kernel, 2 threads per sequence)",
+                         "traffic": traffic, "peak_kind": peak_kind, "kernel": ("lstm_tc3_train_kernel<2,2> (tcgen05 tile kernel, 2 threads per sequence)" if world == 1 else
+                                    "lstm_tc_train_kernel<2> (tcgen05 tile kernel, generation 1: row-sharded table over NVLink)"),
                          "algorithmic_bytes_per_timestep": A_TRAIN_BYTES_PER_TIMESTEP},
         }
         if not args.no_cpu_baseline:

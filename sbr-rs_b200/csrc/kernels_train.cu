@@ -796,10 +796,14 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
         // "2" = kernels_lstm_tc2.cu (+ cp.async prefetch pipeline, merged visits, L2-atomic Adagrad), "2f" = the same
         // with MUFU.TANH gates, "3" / "34" = kernels_lstm_tc3.cu with 2 / 4 threads per sequence
         const char* gen = getenv("SBR_LSTM_TC");
-        if (gen && !strcmp(gen, "1")) *err = launch_lstm_tc(m, p, nt, st);
-        else if (gen && !strcmp(gen, "2")) *err = launch_lstm_tc2(m, p, nt, false, st);
-        else if (gen && !strcmp(gen, "2f")) *err = launch_lstm_tc2(m, p, nt, true, st);
-        else if (gen && !strcmp(gen, "34")) *err = launch_lstm_tc3(m, p, nt, 4, st);
+        // Row-sharded tables (peer rows over NVLink) default to generation 1: it fetches WARP candidates only when a
+        // try needs them, and small remote requests are what NVLink is worst at -- measured on 2 GPUs sharing the
+        // ML-100K-shaped model: generation 1 23.3 M steps/s, generations 2 / 3 (all five candidates prefetched) 13 M.
+        if (!gen) gen = m.gmask != 0 ? "1" : "3";
+        if (!strcmp(gen, "1")) *err = launch_lstm_tc(m, p, nt, st);
+        else if (!strcmp(gen, "2")) *err = launch_lstm_tc2(m, p, nt, false, st);
+        else if (!strcmp(gen, "2f")) *err = launch_lstm_tc2(m, p, nt, true, st);
+        else if (!strcmp(gen, "34")) *err = launch_lstm_tc3(m, p, nt, 4, st);
         else *err = launch_lstm_tc3(m, p, nt, 2, st);
         return 1;
     } else {
