@@ -107,6 +107,35 @@ def cpu_reference_run(num_seqs, steps, warmup, threads, seed=1234):
     return num_seqs * len(times) / sum(times), sum(times) / len(times)
 
 
+class ReplicaSync:
+    """N > 1 on a small (L2-resident) catalogue: every GPU trains a FULL replica on its own users (local Hogwild, the
+    single-GPU kernel at full speed) and after every step the replicas exchange what they changed: the deltas of all
+    parameters and of their Adagrad accumulators are summed over the ranks with one NCCL all-reduce and applied to the
+    common starting point, so that every rank continues from the same model -- the sum of all partitions' updates, as
+    in one big Hogwild run, with a staleness of one step instead of ~0.  (Sharing ONE row-sharded model through NVLink
+    peer mappings -- `SBR_BENCH_MULTI=shared`, DESIGN.md 3.6 -- makes every second row access a small remote request:
+    2 GPUs then run slower than one.)  Host plumbing only: get/set_parameter of the public API + torch.distributed."""
+
+    def __init__(self, model, names, torch, dist):
+        self.m, self.names, self.torch, self.dist = model, names, torch, dist
+        self.dev = "cuda" if torch.cuda.is_available() else "cpu"   # (cpu + gloo in tests/dist_worker.py)
+        self.prev = [model.get_parameter(n) for n in names]
+        self.sizes = [len(p) for p in self.prev]
+        self.bytes_per_sync = 4 * sum(self.sizes)
+
+    def __call__(self):
+        cur = [self.m.get_parameter(n) for n in self.names]
+        delta = self.torch.from_numpy(np.concatenate([c - p for c, p in zip(cur, self.prev)])).to(self.dev)
+        self.dist.all_reduce(delta)
+        delta = delta.cpu().numpy()
+        off = 0
+        for i, n in enumerate(self.names):
+            new = self.prev[i] + delta[off:off + self.sizes[i]]
+            off += self.sizes[i]
+            self.m.set_parameter(n, new)
+            self.prev[i] = new
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -175,7 +204,9 @@ def main():
     hyper = (pkg.lstm.Hyperparameters(NUM_ITEMS, SEQ_LEN).embedding_dim(DIM).learning_rate(LR).l2_penalty(L2)
              .lstm_variant(pkg.LSTMVariant.Normal).loss(pkg.Loss.WARP).optimizer(pkg.Optimizer.Adagrad)
              .parallelism(pkg.Parallelism.Asynchronous).num_epochs(1).num_threads(args.threads).from_seed(seed))
-    if world > 1:
+    multi = os.environ.get("SBR_BENCH_MULTI", "replicas") if world > 1 else "single"
+    sync = None
+    if multi == "shared":
         model = hyper.shard(rank, world).build()
         blobs = [None] * world
         dist.all_gather_object(blobs, model.ipc_export())
@@ -183,12 +214,17 @@ def main():
         dist.barrier()
     else:
         model = hyper.build()
+        if world > 1:
+            names = ["item_embeddings", "item_biases", "lstm_weights", "lstm_biases"]
+            sync = ReplicaSync(model, names + [n + ".s1" for n in names], torch, dist)
 
     # ---------------- device-resident arm: `value` ----------------
     data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=NUM_ITEMS).upload()
     plan = model.fit_plan(data)
     for _ in range(args.warmup):
         plan.run()
+        if sync:
+            sync()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -196,6 +232,8 @@ def main():
     kernel_ms, launches, timesteps = 0.0, 0, 0
     for _ in range(args.steps):
         plan.run()  # blocks until the epoch's kernel has finished (loss read back)
+        if sync:
+            sync()
         st = plan.stats()
         kernel_ms += st["train_kernel_ms"]; launches += st["kernel_launches"]; timesteps += st["timesteps"]
     barrier()
@@ -211,13 +249,19 @@ def main():
     h2d = d2h = 0
     for _ in range(2):
         model.fit(pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=NUM_ITEMS, borrow=True))
+        if sync:
+            sync()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         c = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=NUM_ITEMS, borrow=True)  # host CSR in, nothing resident
         model.fit(c)
+        if sync:
+            sync()
         st = model.last_fit_stats()
         h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
+        if sync:
+            h2d += sync.bytes_per_sync; d2h += sync.bytes_per_sync
         del c
     barrier()
     e2e_wall = max_over_ranks(time.perf_counter() - t0)
@@ -240,7 +284,9 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(config, seqs_per_gpu_per_step=S, partitions_per_gpu=int(partitions),
                            parallelism=("hogwild partitions; one shared model, item table row-sharded over %d GPUs via NVLink peer access" % world)
-                           if world > 1 else "hogwild partitions",
+                           if multi == "shared" else
+                           ("hogwild partitions per GPU; full replica per GPU, deltas of parameters and Adagrad state summed over %d GPUs "
+                            "(one NCCL all-reduce of %d bytes) after every step" % (world, sync.bytes_per_sync)) if world > 1 else "hogwild partitions",
                            l2_policy="id stream (%d MiB/GPU) larger than L2; 215 KB item table is L2-resident by construction"
                                      % (S * SEQ_LEN * 4 >> 20)),
             "timesteps_per_s": value * (SEQ_LEN - 1),
@@ -249,7 +295,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_kind": peak_kind, "kernel": ("lstm_tc3_train_kernel<2,2> (tcgen05 tile kernel, 2 threads per sequence)" if world == 1 else
+                         "traffic": traffic, "peak_kind": peak_kind, "kernel": ("lstm_tc3_train_kernel<2,2> (tcgen05 tile kernel, 2 threads per sequence)" if multi != "shared" else
                                     "lstm_tc_train_kernel<2> (tcgen05 tile kernel, generation 1: row-sharded table over NVLink)"),
                          "algorithmic_bytes_per_timestep": A_TRAIN_BYTES_PER_TIMESTEP},
         }

@@ -50,7 +50,25 @@ def main():
     counts = [None] * world
     dist.all_gather_object(counts, (len(my_ptr) - 1, int(my_ptr[-1])))
     assert sum(c[0] for c in counts) == U and sum(c[1] for c in counts) == int(ptr[-1])
+    # bench.py's replicated multi-GPU mode: after a step every rank holds start + the SUM of all ranks' deltas
+    import bench
+
+    class FakeModel:
+        def __init__(self):
+            self.p = {"a": np.arange(6, dtype=np.float32), "b": np.ones(3, dtype=np.float32)}
+        def get_parameter(self, n):
+            return self.p[n].copy()
+        def set_parameter(self, n, v):
+            self.p[n] = np.asarray(v, dtype=np.float32).copy()
     if not on_gpu:
+        fm = FakeModel()
+        rs = bench.ReplicaSync(fm, ["a", "b"], torch, dist)
+        fm.p["a"] = fm.p["a"] + np.float32(rank + 1)          # this rank's local training moved the parameters
+        fm.p["b"] = fm.p["b"] * np.float32(2 + rank)
+        rs()
+        tot = sum(r + 1 for r in range(world))
+        assert np.allclose(fm.p["a"], np.arange(6) + tot) and np.allclose(fm.p["b"], 1 + sum(1 + r for r in range(world)))
+        assert rs.bytes_per_sync == 36
         blobs = [None] * world
         dist.all_gather_object(blobs, bytes([rank]) * 192)
         assert [b[0] for b in blobs] == list(range(world))
