@@ -34,7 +34,7 @@ def test_mrr_matches_oracle_over_seeds(pkg, oracle, ml100k, kind, epochs, seeds)
     N = 1683
     train = pkg.CompressedInteractions.from_csr(tr[0], tr[1], None, num_items=N)
     test = pkg.CompressedInteractions.from_csr(te[0], te[1], None, num_items=N)
-    g_mrr, o_mrr, h_mrr = [], [], []
+    g_mrr, o_mrr, h_mrr, t_mrr = [], [], [], []
     for s in range(seeds):
         seed = bytes([s + 1] * 16)
         gm, om = make_pair(pkg, oracle, kind, N, 32, 32, loss="warp", optimizer="adagrad", variant="normal", lr=0.16,
@@ -52,8 +52,18 @@ def test_mrr_matches_oracle_over_seeds(pkg, oracle, ml100k, kind, epochs, seeds)
                           l2=4e-4, epochs=epochs, threads=32, seed=seed)
         hm.fit(train)
         h_mrr.append(pkg.mrr_score(hm, test))
+        if kind == "lstm":   # the tensor-core tile kernel (throughput mode: 128 partitions is its minimum), same epochs
+            tm, _ = make_pair(pkg, oracle, kind, N, 32, 32, loss="warp", optimizer="adagrad", variant="normal", lr=0.16,
+                              l2=4e-4, epochs=epochs, threads=128, seed=seed)
+            tm.fit(train)
+            assert tm.last_fit_stats()["partitions"] == 128
+            t_mrr.append(pkg.mrr_score(tm, test))
     out = {"kind": kind, "epochs": epochs, "gpu_1thread": g_mrr, "oracle_1thread": o_mrr, "gpu_32partitions": h_mrr,
            "mean_gpu": float(np.mean(g_mrr)), "mean_oracle": float(np.mean(o_mrr)), "mean_gpu_hogwild32": float(np.mean(h_mrr))}
+    if t_mrr:
+        out["gpu_tile_kernel_128partitions"] = t_mrr
+        out["mean_gpu_tile_kernel_128"] = float(np.mean(t_mrr))
+        assert out["mean_gpu_tile_kernel_128"] > 0.04, out
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     path = os.path.join(ROOT, "gpurun_out", "mrr_parity.json")
     prev = json.load(open(path)) if os.path.exists(path) else {}
