@@ -523,6 +523,50 @@ class _Model:
         st = (C.c_uint32 * 4)(*v)
         _check(lib().sbr_model_set_rng_state(self._m, st))
 
+    # -- checkpoint (the reference derives Serialize/Deserialize for the whole model -- parameters,
+    #    optimizer state inside HogwildParameter, the hyper-parameter rng; lstm.rs:204-210,386-389).  The flat-file form
+    #    here is an .npz of the canonical host-order blobs: every parameter, its optimizer-state slots, the master
+    #    xorshift state and the update counter.  load_state() into a model built from the same hyper-parameters
+    #    continues training exactly where the saved one stopped (optimizer state persists across fit calls, 5. in SURVEY).
+    def parameter_names(self):
+        names = ["item_embeddings", "item_biases"]
+        for extra in ("lstm_weights", "lstm_biases", "alpha"):
+            n = C.c_size_t()
+            if lib().sbr_model_parameter_len(self._m, extra.encode(), C.byref(n)) == 0:
+                names.append(extra)
+        return names
+
+    def state_dict(self):
+        out = {}
+        for n in self.parameter_names():
+            out[n] = self.get_parameter(n)
+            for slot in (".s1", ".s2"):
+                k = C.c_size_t()
+                if lib().sbr_model_parameter_len(self._m, (n + slot).encode(), C.byref(k)) == 0:
+                    try:
+                        out[n + slot] = self.get_parameter(n + slot)
+                    except SbrError:
+                        pass
+        out["rng_state"] = np.asarray(self.rng_state, dtype=np.uint32)
+        out["num_updates"] = np.asarray([self.num_updates], dtype=np.uint64)
+        return out
+
+    def load_state_dict(self, state):
+        for k, v in state.items():
+            if k == "rng_state":
+                self.rng_state = tuple(int(x) for x in v)
+            elif k == "num_updates":
+                self.num_updates = int(np.asarray(v).ravel()[0])
+            else:
+                self.set_parameter(k, v)
+
+    def save_state(self, path):
+        np.savez(path, **self.state_dict())
+
+    def load_state(self, path):
+        with np.load(path) as z:
+            self.load_state_dict({k: z[k] for k in z.files})
+
     def ipc_export(self):
         buf = C.create_string_buffer(lib().sbr_model_ipc_handle_size())
         _check(lib().sbr_model_ipc_export(self._m, buf))
