@@ -146,7 +146,7 @@ sbr_status upload_ids_u32(const uint64_t* src, size_t n, uint32_t* dst, cudaStre
             for (size_t i = lo; i < hi; ++i) { const uint64_t v = src[done + i]; bd |= (uint64_t)(v >= bound); out[i] = (uint32_t)v; }
             if (bd) bad.store(1);
         };
-        const size_t nth = cnt >= (1u << 20) ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        const size_t nth = cnt >= (1u << 20) ? std::min<size_t>(12, std::max(1u, std::thread::hardware_concurrency())) : 1;
         if (nth <= 1) narrow(0, cnt);
         else {
             std::vector<std::thread> th;
@@ -747,27 +747,45 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     });
     struct Joiner { std::future<sbr_status>& f; cudaEvent_t& e; bool taken = false;
                     ~Joiner() { if (f.valid()) f.wait(); if (e && !taken) cudaEventDestroy(e); } } joiner{up, ev_begin};
-    // sequence_model.rs:76-83: chunk every user, keep len > 2
+    // sequence_model.rs:76-83: chunk every user, keep len > 2.  data.rs:406-432: the FIRST chunk is the short one
+    // (len % T items, if that is not 0), every later chunk has exactly T items -- one division per user.
     std::vector<uint64_t> starts; std::vector<uint32_t> lens;
+    starts.reserve(c->nnz_ / T + c->num_users); lens.reserve(c->nnz_ / T + c->num_users);
     uint64_t timesteps = 0;
     for (size_t u = 0; u < c->num_users; ++u) {
         const size_t b = c->up_[u], len = c->up_[u + 1] - b;
+        if (len == 0) continue;
         size_t idx = 0;
-        while (idx < len) {
-            const size_t mod = (len - idx) % T;
-            const size_t cs = mod == 0 ? T : mod;
-            if (cs > 2) { starts.push_back(b + idx); lens.push_back((uint32_t)cs); }
-            idx += cs;
-        }
+        const size_t first = len % T;
+        if (first != 0) { if (first > 2) { starts.push_back(b); lens.push_back((uint32_t)first); } idx = first; }
+        if (T > 2) for (; idx < len; idx += T) { starts.push_back(b + idx); lens.push_back((uint32_t)T); }
     }
     const size_t nsub = starts.size();
     if (nsub == 0) return fail(SBR_ERR_NO_INTERACTIONS, "No interactions were supplied.");  // :86-88
     if (nsub > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "too many sub-sequences");
     std::lock_guard<std::mutex> lk(m->mu);
-    // :84 parameters.rng().shuffle(&mut subsequences)
+    // :84 parameters.rng().shuffle(&mut subsequences): Fisher-Yates from the top.  The swap partners depend on the rng
+    // stream only, so they are drawn 16 iterations ahead (same stream, same order) and their cache lines requested early.
     std::vector<uint32_t> order(nsub);
     for (size_t i = 0; i < nsub; ++i) order[i] = (uint32_t)i;
-    for (size_t i = nsub; i >= 2;) { i -= 1; const size_t j = (size_t)xs_gen_below(m->rng, (uint64_t)i + 1); std::swap(order[i], order[j]); }
+    {
+        constexpr size_t K = 16;
+        size_t js[K];
+        size_t i = nsub, drawn = nsub;
+        auto draw = [&]() {
+            drawn -= 1;
+            const size_t j = (size_t)xs_gen_below(m->rng, (uint64_t)drawn + 1);
+            js[drawn % K] = j;
+            __builtin_prefetch(order.data() + j, 1);
+        };
+        for (size_t k = 0; k < K && drawn >= 2; ++k) draw();
+        while (i >= 2) {
+            i -= 1;
+            const size_t j = js[i % K];
+            if (drawn >= 2) draw();
+            std::swap(order[i], order[j]);
+        }
+    }
     // :90-98 partitions
     size_t P = m->h.num_threads;
     if (P == 0) {
@@ -784,7 +802,8 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
         uint64_t k = 0; for (int i = 0; i < 8; ++i) k |= (uint64_t)seed[i] << (8 * i);
         keys[p] = k;
     }
-    for (size_t i = 0; i < P * n; ++i) timesteps += lens[order[i]] - 1;
+    for (size_t i = 0; i < nsub; ++i) timesteps += lens[i] - 1;                       // all sub-sequences ...
+    for (size_t i = P * n; i < nsub; ++i) timesteps -= lens[order[i]] - 1;            // ... minus the remainder the zip at :94-96 drops
     const double t1 = now_ms();
 
     sbr_fit_plan* pl = new (std::nothrow) sbr_fit_plan();
