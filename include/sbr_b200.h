@@ -59,6 +59,11 @@ sbr_status sbr_set_device(int device);
 /* Interactions::to_compressed (data.rs:180-182, 236-265): stable sort by (user, timestamp), histogram, prefix sum. */
 sbr_status sbr_compressed_from_triplets(const uint64_t* user_ids, const uint64_t* item_ids, const uint64_t* timestamps,
                                         size_t nnz, size_t num_users, size_t num_items, sbr_compressed** out);
+/* The same on the device: stable LSD radix sort by timestamp then by user, gather, histogram, scan.
+ * Result identical to sbr_compressed_from_triplets including the order of (user, timestamp) ties (data.rs:240 sorts
+ * stably); the narrowed item-id stream stays resident in HBM, so the first fit() uploads nothing.  Needs the device. */
+sbr_status sbr_compressed_from_triplets_device(const uint64_t* user_ids, const uint64_t* item_ids, const uint64_t* timestamps,
+                                               size_t nnz, size_t num_users, size_t num_items, sbr_compressed** out);
 /* Adopt an existing CSR (the three Vec fields at data.rs:231-233). timestamps may be NULL. Copies. */
 sbr_status sbr_compressed_from_csr(const uint64_t* user_pointers, const uint64_t* item_ids, const uint64_t* timestamps,
                                    size_t num_users, size_t num_items, sbr_compressed** out);

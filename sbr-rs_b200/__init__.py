@@ -31,7 +31,7 @@ SBR_ERR_CUDA, SBR_ERR_NCCL, SBR_ERR_UNSUPPORTED = 4, 5, 6
 # every symbol include/sbr_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "sbr_last_error_string", "sbr_device_count", "sbr_set_device",
-    "sbr_compressed_from_triplets", "sbr_compressed_from_csr", "sbr_compressed_borrow_csr", "sbr_compressed_num_users", "sbr_compressed_num_items",
+    "sbr_compressed_from_triplets", "sbr_compressed_from_triplets_device", "sbr_compressed_from_csr", "sbr_compressed_borrow_csr", "sbr_compressed_num_users", "sbr_compressed_num_items",
     "sbr_compressed_len", "sbr_compressed_borrow", "sbr_compressed_user_chunks", "sbr_compressed_upload",
     "sbr_compressed_free",
     "sbr_lstm_hyperparameters_new", "sbr_ewma_hyperparameters_new", "sbr_hyper_learning_rate", "sbr_hyper_l2_penalty",
@@ -96,6 +96,7 @@ def lib():
     vp = C.c_void_p
     L.sbr_last_error_string.restype = C.c_char_p
     L.sbr_compressed_from_triplets.argtypes = [u64p, u64p, u64p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(vp)]
+    L.sbr_compressed_from_triplets_device.argtypes = [u64p, u64p, u64p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(vp)]
     L.sbr_compressed_from_csr.argtypes = [u64p, u64p, u64p, C.c_size_t, C.c_size_t, C.POINTER(vp)]
     L.sbr_compressed_borrow_csr.argtypes = [u64p, u64p, u64p, C.c_size_t, C.c_size_t, C.POINTER(vp)]
     for f in ("num_users", "num_items", "len"):
@@ -289,10 +290,11 @@ class CompressedInteractions:
         self._h = handle
 
     @classmethod
-    def _from_triplets(cls, u, i, t, num_users, num_items):
+    def _from_triplets(cls, u, i, t, num_users, num_items, device=False):
+        """device=True: the CSR is built on the GPU (sbr_compressed_from_triplets_device) and stays resident."""
         h = C.c_void_p()
-        _check(lib().sbr_compressed_from_triplets(_p(u, u64p), _p(i, u64p), _p(t, u64p), len(u), num_users, num_items,
-                                                  C.byref(h)))
+        fn = lib().sbr_compressed_from_triplets_device if device else lib().sbr_compressed_from_triplets
+        _check(fn(_p(u, u64p), _p(i, u64p), _p(t, u64p), len(u), num_users, num_items, C.byref(h)))
         return cls(h)
 
     @classmethod

@@ -389,6 +389,31 @@ sbr_status sbr_compressed_from_triplets(const uint64_t* user_ids, const uint64_t
     return SBR_OK;
 }
 
+sbr_status sbr_compressed_from_triplets_device(const uint64_t* user_ids, const uint64_t* item_ids, const uint64_t* timestamps,
+                                               size_t nnz, size_t num_users, size_t num_items, sbr_compressed** out) {
+    if (!out || (nnz && (!user_ids || !item_ids || !timestamps))) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if (num_items > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "num_items must fit in 32 bits");
+    sbr_status s = require_device();
+    if (s) return s;
+    sbr_compressed* c = new (std::nothrow) sbr_compressed();
+    if (!c) return fail(SBR_ERR_INVALID_ARGUMENT, "out of memory");
+    c->num_users = num_users; c->num_items = num_items;
+    c->user_ptr.assign(num_users + 1, 0);
+    c->item_ids.resize(nnz); c->timestamps.resize(nnz);
+    uint32_t* d_ids = nullptr; uint64_t* d_ptr = nullptr;
+    cudaError_t e = pool_alloc(&d_ids, std::max<size_t>(nnz, 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = pool_alloc(&d_ptr, (num_users + 1) * sizeof(uint64_t));
+    if (e != cudaSuccess) { g_pool.release(d_ids); g_pool.release(d_ptr); delete c; return cuda_fail(e, "cudaMalloc CSR mirror"); }
+    std::string err;
+    const int rc = device_csr_build(user_ids, item_ids, timestamps, nnz, num_users, num_items, c->user_ptr.data(), c->item_ids.data(),
+                                    c->timestamps.data(), d_ids, d_ptr, nullptr, &err);
+    if (rc) { g_pool.release(d_ids); g_pool.release(d_ptr); delete c; return fail(rc == 2 ? SBR_ERR_INVALID_ARGUMENT : SBR_ERR_CUDA, err); }
+    c->own_views();
+    c->d_item_ids = d_ids; c->d_user_ptr = d_ptr;   // the CSR is already resident: the first fit() uploads nothing
+    *out = c;
+    return SBR_OK;
+}
+
 sbr_status sbr_compressed_from_csr(const uint64_t* user_pointers, const uint64_t* item_ids, const uint64_t* timestamps,
                                    size_t num_users, size_t num_items, sbr_compressed** out) {
     if (!out || !user_pointers) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");

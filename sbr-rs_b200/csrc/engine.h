@@ -79,6 +79,11 @@ namespace sbr {
 int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm, int rank, int world, uint64_t num_updates,
                   cudaStream_t st, int* launches, uint64_t* rounds_out, std::string* err);
 
+// Interactions::to_compressed on the device (data_prep.cu): 0 ok, 1 CUDA error, 2 invalid argument
+int device_csr_build(const uint64_t* h_user, const uint64_t* h_item, const uint64_t* h_ts, size_t nnz, size_t num_users, size_t num_items,
+                     uint64_t* h_user_ptr, uint64_t* h_item_out, uint64_t* h_ts_out, uint32_t* d_item_u32, uint64_t* d_user_ptr,
+                     cudaStream_t st, std::string* err);
+
 cudaError_t launch_gather_rows(const ModelDev& m, const uint32_t* ids_dev, size_t n, float* out_dev, cudaStream_t st);
 cudaError_t launch_user_representations(const ModelDev& m, const uint64_t* ptr_dev, const uint32_t* ids_dev, size_t num_users,
                                         float* out_dev, cudaStream_t st);
