@@ -170,6 +170,12 @@ typedef struct {
     double host_prepare_ms;  /* sub-sequence build + shuffle + partitioning on the host */
 } sbr_fit_stats;
 
+/* Host-only test hook: the schedule fit() builds from a CSR -- sequence_model.rs:76-84: chunks of every user
+ * (data.rs:406-432), the len > 2 filter (:81) and the master-rng shuffle (:84).  Needs no device.  `rng_state` is the
+ * xorshift128 state (in: before the shuffle, out: after it); with cap < *nsub only the count is returned. */
+sbr_status sbr_host_schedule(const sbr_compressed* c, size_t max_sequence_length, uint32_t rng_state[4], uint64_t* starts,
+                             uint32_t* lens, uint32_t* order, size_t cap, size_t* nsub);
+
 /* Split of sbr_model_fit into "stage once" + "run": create does sequence_model.rs:74-98 (sub-sequences, shuffle,
  * partitions, per-partition rngs) and puts everything in HBM; run does :100-175 for num_epochs epochs. */
 sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* interactions, sbr_fit_plan** out);

@@ -32,7 +32,7 @@ SBR_ERR_CUDA, SBR_ERR_NCCL, SBR_ERR_UNSUPPORTED = 4, 5, 6
 EXPORTS = [
     "sbr_last_error_string", "sbr_device_count", "sbr_set_device",
     "sbr_compressed_from_triplets", "sbr_compressed_from_triplets_device", "sbr_compressed_from_csr", "sbr_compressed_borrow_csr", "sbr_compressed_num_users", "sbr_compressed_num_items",
-    "sbr_compressed_len", "sbr_compressed_borrow", "sbr_compressed_user_chunks", "sbr_compressed_upload",
+    "sbr_compressed_len", "sbr_compressed_borrow", "sbr_compressed_user_chunks", "sbr_compressed_upload", "sbr_host_schedule",
     "sbr_compressed_free",
     "sbr_lstm_hyperparameters_new", "sbr_ewma_hyperparameters_new", "sbr_hyper_learning_rate", "sbr_hyper_l2_penalty",
     "sbr_hyper_embedding_dim", "sbr_hyper_num_epochs", "sbr_hyper_loss", "sbr_hyper_lstm_variant",
@@ -105,6 +105,8 @@ def lib():
     L.sbr_compressed_borrow.argtypes = [vp, C.POINTER(u64p), C.POINTER(u64p), C.POINTER(u64p)]
     L.sbr_compressed_user_chunks.argtypes = [vp, C.c_size_t, C.c_size_t, u64p, u64p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.sbr_compressed_upload.argtypes = [vp]
+    L.sbr_host_schedule.argtypes = [vp, C.c_size_t, C.POINTER(C.c_uint32), u64p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_size_t,
+                                    C.POINTER(C.c_size_t)]
     L.sbr_compressed_free.argtypes = [vp]
     L.sbr_lstm_hyperparameters_new.restype = vp
     L.sbr_lstm_hyperparameters_new.argtypes = [C.c_size_t, C.c_size_t]
@@ -356,6 +358,17 @@ class CompressedInteractions:
     def upload(self):
         _check(lib().sbr_compressed_upload(self._h))
         return self
+
+    def host_schedule(self, max_sequence_length, rng_state):
+        """sequence_model.rs:76-84 as fit() does it on the host (sbr_host_schedule; needs no device):
+        returns (starts, lens, shuffled order, rng state after the shuffle)."""
+        st = (C.c_uint32 * 4)(*[int(x) for x in rng_state])
+        n = C.c_size_t()
+        _check(lib().sbr_host_schedule(self._h, max_sequence_length, st, None, None, None, 0, C.byref(n)))
+        starts = np.zeros(n.value, dtype=np.uint64); lens = np.zeros(n.value, dtype=np.uint32); order = np.zeros(n.value, dtype=np.uint32)
+        _check(lib().sbr_host_schedule(self._h, max_sequence_length, st, _p(starts, u64p), lens.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                       order.ctypes.data_as(C.POINTER(C.c_uint32)), n.value, C.byref(n)))
+        return starts, lens, order, tuple(int(x) for x in st)
 
 
 # ------------------------------------------------------------------------------------------------ models ----

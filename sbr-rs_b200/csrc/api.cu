@@ -313,6 +313,47 @@ sbr_status ensure_uploaded(const sbr_compressed* c, cudaStream_t st) {
     return SBR_OK;
 }
 
+// sequence_model.rs:76-84 on the host: chunk every user (data.rs:406-432: the FIRST chunk is the short one -- len % T
+// items, if that is not 0 -- every later chunk has exactly T items: one division per user), keep len > 2 (:81), then
+// parameters.rng().shuffle(&mut subsequences) (:84): Fisher-Yates from the top.  The swap partners depend on the rng
+// stream only, so they are drawn 16 iterations ahead (same stream, same order) and their cache lines requested early.
+sbr_status host_schedule(const sbr_compressed* c, size_t T, XorShift& rng, std::vector<uint64_t>& starts, std::vector<uint32_t>& lens,
+                         std::vector<uint32_t>& order) {
+    if (T == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "max_sequence_length must be positive");
+    starts.clear(); lens.clear();
+    starts.reserve(c->nnz_ / T + c->num_users); lens.reserve(c->nnz_ / T + c->num_users);
+    for (size_t u = 0; u < c->num_users; ++u) {
+        const size_t b = c->up_[u], len = c->up_[u + 1] - b;
+        if (len == 0) continue;
+        size_t idx = 0;
+        const size_t first = len % T;
+        if (first != 0) { if (first > 2) { starts.push_back(b); lens.push_back((uint32_t)first); } idx = first; }
+        if (T > 2) for (; idx < len; idx += T) { starts.push_back(b + idx); lens.push_back((uint32_t)T); }
+    }
+    const size_t nsub = starts.size();
+    if (nsub == 0) return fail(SBR_ERR_NO_INTERACTIONS, "No interactions were supplied.");  // :86-88
+    if (nsub > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "too many sub-sequences");
+    order.resize(nsub);
+    for (size_t i = 0; i < nsub; ++i) order[i] = (uint32_t)i;
+    constexpr size_t K = 16;
+    size_t js[K];
+    size_t i = nsub, drawn = nsub;
+    auto draw = [&]() {
+        drawn -= 1;
+        const size_t j = (size_t)xs_gen_below(rng, (uint64_t)drawn + 1);
+        js[drawn % K] = j;
+        __builtin_prefetch(order.data() + j, 1);
+    };
+    for (size_t k = 0; k < K && drawn >= 2; ++k) draw();
+    while (i >= 2) {
+        i -= 1;
+        const size_t j = js[i % K];
+        if (drawn >= 2) draw();
+        std::swap(order[i], order[j]);
+    }
+    return SBR_OK;
+}
+
 struct ParamRef { int kind; int slot; size_t off, len; };  // kind 0: E rows, 1: bias, 2: dense
 
 sbr_status resolve_param(const sbr_model* m, const char* name, ParamRef* out) {
@@ -750,6 +791,26 @@ sbr_status sbr_model_set_rng_state(sbr_model* m, const uint32_t state[4]) {
     return SBR_OK;
 }
 
+// host-only view of the schedule that fit() builds (no device needed): lets CPU-only CI pin the chunker / filter /
+// master shuffle against the oracle
+sbr_status sbr_host_schedule(const sbr_compressed* c, size_t max_sequence_length, uint32_t rng_state[4], uint64_t* starts, uint32_t* lens,
+                             uint32_t* order, size_t cap, size_t* nsub) {
+    if (!c || !rng_state || !nsub) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if ((rng_state[0] | rng_state[1] | rng_state[2] | rng_state[3]) == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "xorshift state must not be all zero");
+    XorShift rng; rng.x = rng_state[0]; rng.y = rng_state[1]; rng.z = rng_state[2]; rng.w = rng_state[3];
+    std::vector<uint64_t> st; std::vector<uint32_t> ln, od;
+    sbr_status s = host_schedule(c, max_sequence_length, rng, st, ln, od);
+    if (s) return s;
+    *nsub = st.size();
+    if (starts && lens && order && cap >= st.size()) {
+        std::memcpy(starts, st.data(), st.size() * sizeof(uint64_t));
+        std::memcpy(lens, ln.data(), ln.size() * sizeof(uint32_t));
+        std::memcpy(order, od.data(), od.size() * sizeof(uint32_t));
+        rng_state[0] = rng.x; rng_state[1] = rng.y; rng_state[2] = rng.z; rng_state[3] = rng.w;
+    }
+    return SBR_OK;
+}
+
 // --------------------------------------------------------------------------------------------------- fit ----
 sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_plan** out) {
     if (!m || !c || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
@@ -772,45 +833,13 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     });
     struct Joiner { std::future<sbr_status>& f; cudaEvent_t& e; bool taken = false;
                     ~Joiner() { if (f.valid()) f.wait(); if (e && !taken) cudaEventDestroy(e); } } joiner{up, ev_begin};
-    // sequence_model.rs:76-83: chunk every user, keep len > 2.  data.rs:406-432: the FIRST chunk is the short one
-    // (len % T items, if that is not 0), every later chunk has exactly T items -- one division per user.
-    std::vector<uint64_t> starts; std::vector<uint32_t> lens;
-    starts.reserve(c->nnz_ / T + c->num_users); lens.reserve(c->nnz_ / T + c->num_users);
+    // sequence_model.rs:76-84: sub-sequences of every user, filtered, shuffled with the master rng
+    std::vector<uint64_t> starts; std::vector<uint32_t> lens; std::vector<uint32_t> order;
     uint64_t timesteps = 0;
-    for (size_t u = 0; u < c->num_users; ++u) {
-        const size_t b = c->up_[u], len = c->up_[u + 1] - b;
-        if (len == 0) continue;
-        size_t idx = 0;
-        const size_t first = len % T;
-        if (first != 0) { if (first > 2) { starts.push_back(b); lens.push_back((uint32_t)first); } idx = first; }
-        if (T > 2) for (; idx < len; idx += T) { starts.push_back(b + idx); lens.push_back((uint32_t)T); }
-    }
-    const size_t nsub = starts.size();
-    if (nsub == 0) return fail(SBR_ERR_NO_INTERACTIONS, "No interactions were supplied.");  // :86-88
-    if (nsub > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "too many sub-sequences");
     std::lock_guard<std::mutex> lk(m->mu);
-    // :84 parameters.rng().shuffle(&mut subsequences): Fisher-Yates from the top.  The swap partners depend on the rng
-    // stream only, so they are drawn 16 iterations ahead (same stream, same order) and their cache lines requested early.
-    std::vector<uint32_t> order(nsub);
-    for (size_t i = 0; i < nsub; ++i) order[i] = (uint32_t)i;
-    {
-        constexpr size_t K = 16;
-        size_t js[K];
-        size_t i = nsub, drawn = nsub;
-        auto draw = [&]() {
-            drawn -= 1;
-            const size_t j = (size_t)xs_gen_below(m->rng, (uint64_t)drawn + 1);
-            js[drawn % K] = j;
-            __builtin_prefetch(order.data() + j, 1);
-        };
-        for (size_t k = 0; k < K && drawn >= 2; ++k) draw();
-        while (i >= 2) {
-            i -= 1;
-            const size_t j = js[i % K];
-            if (drawn >= 2) draw();
-            std::swap(order[i], order[j]);
-        }
-    }
+    s = host_schedule(c, T, m->rng, starts, lens, order);
+    if (s) return s;
+    const size_t nsub = starts.size();
     // :90-98 partitions
     size_t P = m->h.num_threads;
     if (P == 0) {

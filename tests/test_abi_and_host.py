@@ -128,3 +128,37 @@ def test_product_never_touches_the_oracle():
     import subprocess
     out = subprocess.run(["nm", "-D", os.path.join(ROOT, "sbr-rs_b200", "libsbr_b200.so")], capture_output=True, text=True)
     assert "sbo_" not in out.stdout
+
+
+@pytest.mark.parametrize("T,min_len,max_len", [(3, 0, 11), (7, 0, 40), (32, 1, 100), (32, 32, 32), (200, 0, 450)])
+def test_host_schedule_equals_oracle(pkg, oracle, T, min_len, max_len):
+    """The schedule fit() builds on the host -- chunks of every user with the first chunk the short one
+    (data.rs:406-432), the len > 2 filter (sequence_model.rs:81), the master-rng Fisher-Yates shuffle (:84) -- is
+    bit-identical to the oracle's restatement (sbo_subsequences + sbo_shuffle_u32), rng state afterwards included.
+    (The library draws the swap partners 16 iterations ahead and chunks with one division per user.)"""
+    import ctypes as C
+    rng = np.random.default_rng(T * 1000 + max_len)
+    U = 3000
+    lens = rng.integers(min_len, max_len + 1, size=U)
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    ids = rng.integers(1, 50, size=int(ptr[-1])).astype(np.uint64)
+    data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=50)
+    seed = bytes(range(7, 23))
+    r = oracle.make_rng(seed)
+    state0 = (r.x, r.y, r.z, r.w)
+    starts, slens, order, state1 = data.host_schedule(T, state0)
+    ost, oln = oracle.subsequences(ptr, T)
+    assert np.array_equal(starts, ost) and np.array_equal(slens, oln)
+    oorder = np.arange(len(ost), dtype=np.uint32)
+    oracle.lib().sbo_shuffle_u32(C.byref(r), oorder.ctypes.data_as(oracle.u32p), len(oorder))
+    assert np.array_equal(order, oorder)
+    assert state1 == (r.x, r.y, r.z, r.w)
+    assert int(slens.min()) > 2 and int(slens.max()) <= T
+
+
+def test_host_schedule_empty_is_no_interactions(pkg):
+    ptr = np.array([0, 2, 3, 5], dtype=np.uint64)          # every user has <= 2 interactions: nothing survives the filter
+    ids = np.array([1, 2, 3, 4, 5], dtype=np.uint64)
+    data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=10)
+    with pytest.raises(pkg.NoInteractions):                # FittingError::NoInteractions (sequence_model.rs:86-88)
+        data.host_schedule(8, (1, 2, 3, 4))
