@@ -102,8 +102,8 @@ def test_one_round_matches_oracle_gradients(pkg, oracle, monkeypatch, gen, P, va
     assert np.array_equal(gE[untouched], E0[untouched])          # rows nobody named are bit-identical
 
 
-@pytest.mark.parametrize("loss", ["bpr", "warp"])
-def test_tile_kernel_learns_like_the_exact_path(pkg, oracle, loss):
+@pytest.mark.parametrize("loss,optimizer,lr", [("bpr", "adagrad", 0.05), ("warp", "adagrad", 0.05), ("hinge", "adam", 0.002)])
+def test_tile_kernel_learns_like_the_exact_path(pkg, oracle, loss, optimizer, lr):
     """Statistical parity on an ML-100K-shaped stream: per-epoch losses of the tile kernel (256 partitions) track the
     exact FFMA kernel run with the same partition count, and parameters stay finite."""
     import os
@@ -116,7 +116,7 @@ def test_tile_kernel_learns_like_the_exact_path(pkg, oracle, loss):
             os.environ["SBR_LSTM_KERNEL"] = "ffma"
         else:
             os.environ.pop("SBR_LSTM_KERNEL", None)
-        gm, _ = make_pair(pkg, oracle, "lstm", N, T, D, loss=loss, optimizer="adagrad", variant="normal", lr=0.05,
+        gm, _ = make_pair(pkg, oracle, "lstm", N, T, D, loss=loss, optimizer=optimizer, variant="normal", lr=lr,
                           l2=1e-4, epochs=1, threads=256)
         data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
         losses[kern] = [gm.fit(data) / 256 for _ in range(6)]
@@ -125,4 +125,5 @@ def test_tile_kernel_learns_like_the_exact_path(pkg, oracle, loss):
     os.environ.pop("SBR_LSTM_KERNEL", None)
     a, b = np.array(losses["ffma"]), np.array(losses["tc"])
     assert b[-1] < b[0]
-    assert np.max(np.abs(a - b)) < 0.02, (a, b)
+    # Adam's normalised steps amplify the bf16 / tf32 rounding of the first gradients: wider band for that case
+    assert np.max(np.abs(a - b)) < (0.02 if optimizer == "adagrad" else 0.08), (a, b)
