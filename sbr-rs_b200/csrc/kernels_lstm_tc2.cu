@@ -159,7 +159,7 @@ __device__ __forceinline__ void slice_read_row(const Slice& s, int lane, float (
 // sequences of the warp naming the same row is the usual Hogwild race (last store wins).
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void coop_visits(const ModelDev& m, const Table& tb, uint32_t neg, uint32_t out, uint32_t fl, int lane,
-                                            const Slice& gh, const Slice& dx, const OptCfg& o, const bool nostore = false, const bool noatom = false) {
+                                            const Slice& gh, const Slice& dx, const OptCfg& o, const bool noatom = false) {
     const int rl = lane & 7, ch = lane >> 3;
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
@@ -241,10 +241,8 @@ __device__ __forceinline__ void coop_visits(const ModelDev& m, const Table& tb, 
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (o.adam) v = __ldcg(reinterpret_cast<const float4*>(rn[gg] + hf * 16 + 2 * kD));
                 apply4(wn[it], sn[it], v, g4, 1.0f, o);
-                if (!nostore) {
                 __stcg(reinterpret_cast<float4*>(rn[gg] + hf * 16), wn[it]);
                 __stcg(reinterpret_cast<float4*>(rn[gg] + hf * 16 + kD), sn[it]);
-                } else if (wn[it].x == 12345.678f && sn[it].y == 1.2345f) __stcg(reinterpret_cast<float4*>(rn[gg] + hf * 16), wn[it]);
                 if (o.adam) __stcg(reinterpret_cast<float4*>(rn[gg] + hf * 16 + 2 * kD), v);
             }
             if (f[gg] & 2u) {
@@ -256,10 +254,8 @@ __device__ __forceinline__ void coop_visits(const ModelDev& m, const Table& tb, 
                 }
                 if (f[gg] & 8u) apply4(wo[it], so[it], v, g4, 1.0f, o);
                 if (f[gg] & 16u) apply4(wo[it], so[it], v, g4, -1.0f, o);
-                if (!nostore) {
                 __stcg(reinterpret_cast<float4*>(ro[gg] + hf * 16), wo[it]);
                 __stcg(reinterpret_cast<float4*>(ro[gg] + hf * 16 + kD), so[it]);
-                } else if (wo[it].x == 12345.678f && so[it].y == 1.2345f) __stcg(reinterpret_cast<float4*>(ro[gg] + hf * 16), wo[it]);
                 if (o.adam) __stcg(reinterpret_cast<float4*>(ro[gg] + hf * 16 + 2 * kD), v);
             }
         }
@@ -718,7 +714,7 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                     const uint32_t fl = (act && !triple ? 1u : 0u) | ((act || has_dx) ? 2u : 0u) | (has_dx ? 4u : 0u) | (triple ? 8u : 0u) | (act ? 16u : 0u);
                     float4* rn = bias_rec(m, neg); float4* ro = bias_rec(m, out);
                     float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
-                    const bool bv = act && !(pl.dbg_flags & 4);
+                    const bool bv = act;
                     const bool batom = !o.adam && !(pl.dbg_flags & 8) && !m.hbm_resident;
                     float* fn_ = reinterpret_cast<float*>(rn); float* fo_ = reinterpret_cast<float*>(ro);
                     if (bv) {
@@ -727,7 +723,7 @@ __global__ void __launch_bounds__(128 * NT, 1) lstm_tc2_train_kernel(ModelDev m,
                             if (neg != out) { bb.x = __ldcg(fo_); bb.y = atomicAdd(fo_ + 1, g * g); }
                         } else { ba = __ldcg(rn); if (neg != out) bb = __ldcg(ro); }
                     }
-                    coop_visits(m, tb, neg, out, (pl.dbg_flags & 1) ? 0u : fl, lane, SZ0, SZ1, o, (pl.dbg_flags & 2) != 0, (pl.dbg_flags & 8) != 0 || m.hbm_resident != 0);
+                    coop_visits(m, tb, neg, out, fl, lane, SZ0, SZ1, o, (pl.dbg_flags & 8) != 0 || m.hbm_resident != 0);
                     if (bv) {   // b[neg] += step(+g), b[out] += step(-g)
                         const float4 a0 = ba, b0 = bb;
                         if (neg != out) {
