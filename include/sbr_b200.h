@@ -170,6 +170,15 @@ typedef struct {
     double host_prepare_ms;  /* sub-sequence build + shuffle + partitioning on the host */
 } sbr_fit_stats;
 
+/* data.rs:69-88 user_based_split (no user in both sets): out_is_train[i] = SipHash-2-4(key_0, key_1, user_ids[i]) % 100000 >
+ * (test_fraction * 100000) as u64, key_0 / key_1 = two Uniform<u64> draws from the xorshift128 state `rng_state` (in / out).
+ * Host-only: data preparation of the reference's tests and examples (lstm.rs:428-430). */
+sbr_status sbr_user_based_split(const uint64_t* user_ids, size_t nnz, uint32_t rng_state[4], float test_fraction,
+                                uint8_t* out_is_train);
+/* data.rs:54-64 train_test_split: shuffle, then the first (test_fraction * nnz) as usize shuffled interactions are the
+ * test set.  perm[k] = original index of the k-th shuffled interaction; perm[0 .. *num_test) is test, the rest train. */
+sbr_status sbr_train_test_split(size_t nnz, uint32_t rng_state[4], float test_fraction, uint64_t* perm, size_t* num_test);
+
 /* Host-only test hook: the schedule fit() builds from a CSR -- sequence_model.rs:76-84: chunks of every user
  * (data.rs:406-432), the len > 2 filter (:81) and the master-rng shuffle (:84).  Needs no device.  `rng_state` is the
  * xorshift128 state (in: before the shuffle, out: after it); with cap < *nsub only the count is returned. */

@@ -32,7 +32,7 @@ SBR_ERR_CUDA, SBR_ERR_NCCL, SBR_ERR_UNSUPPORTED = 4, 5, 6
 EXPORTS = [
     "sbr_last_error_string", "sbr_device_count", "sbr_set_device",
     "sbr_compressed_from_triplets", "sbr_compressed_from_triplets_device", "sbr_compressed_from_csr", "sbr_compressed_borrow_csr", "sbr_compressed_num_users", "sbr_compressed_num_items",
-    "sbr_compressed_len", "sbr_compressed_borrow", "sbr_compressed_user_chunks", "sbr_compressed_upload", "sbr_host_schedule",
+    "sbr_compressed_len", "sbr_compressed_borrow", "sbr_compressed_user_chunks", "sbr_compressed_upload", "sbr_host_schedule", "sbr_user_based_split", "sbr_train_test_split",
     "sbr_compressed_free",
     "sbr_lstm_hyperparameters_new", "sbr_ewma_hyperparameters_new", "sbr_hyper_learning_rate", "sbr_hyper_l2_penalty",
     "sbr_hyper_embedding_dim", "sbr_hyper_num_epochs", "sbr_hyper_loss", "sbr_hyper_lstm_variant",
@@ -105,6 +105,8 @@ def lib():
     L.sbr_compressed_borrow.argtypes = [vp, C.POINTER(u64p), C.POINTER(u64p), C.POINTER(u64p)]
     L.sbr_compressed_user_chunks.argtypes = [vp, C.c_size_t, C.c_size_t, u64p, u64p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.sbr_compressed_upload.argtypes = [vp]
+    L.sbr_user_based_split.argtypes = [u64p, C.c_size_t, C.POINTER(C.c_uint32), C.c_float, C.POINTER(C.c_uint8)]
+    L.sbr_train_test_split.argtypes = [C.c_size_t, C.POINTER(C.c_uint32), C.c_float, u64p, C.POINTER(C.c_size_t)]
     L.sbr_host_schedule.argtypes = [vp, C.c_size_t, C.POINTER(C.c_uint32), u64p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_size_t,
                                     C.POINTER(C.c_size_t)]
     L.sbr_compressed_free.argtypes = [vp]
@@ -369,6 +371,24 @@ class CompressedInteractions:
         _check(lib().sbr_host_schedule(self._h, max_sequence_length, st, _p(starts, u64p), lens.ctypes.data_as(C.POINTER(C.c_uint32)),
                                        order.ctypes.data_as(C.POINTER(C.c_uint32)), n.value, C.byref(n)))
         return starts, lens, order, tuple(int(x) for x in st)
+
+
+def user_based_split(user_ids, rng_state, test_fraction):
+    """data.rs:69-88: boolean mask is_train per interaction (no user in both sets) and the rng state afterwards."""
+    u = _u64(user_ids)
+    st = (C.c_uint32 * 4)(*[int(x) for x in rng_state])
+    out = np.zeros(len(u), dtype=np.uint8)
+    _check(lib().sbr_user_based_split(_p(u, u64p), len(u), st, float(test_fraction), out.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return out.astype(bool), tuple(int(x) for x in st)
+
+
+def train_test_split(nnz, rng_state, test_fraction):
+    """data.rs:54-64: (train_indices, test_indices) into the original interactions and the rng state afterwards."""
+    st = (C.c_uint32 * 4)(*[int(x) for x in rng_state])
+    perm = np.zeros(int(nnz), dtype=np.uint64)
+    nt = C.c_size_t()
+    _check(lib().sbr_train_test_split(int(nnz), st, float(test_fraction), _p(perm, u64p), C.byref(nt)))
+    return perm[nt.value:], perm[:nt.value], tuple(int(x) for x in st)
 
 
 # ------------------------------------------------------------------------------------------------ models ----

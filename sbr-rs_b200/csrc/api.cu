@@ -791,6 +791,50 @@ sbr_status sbr_model_set_rng_state(sbr_model* m, const uint32_t state[4]) {
     return SBR_OK;
 }
 
+// ---------------------------------------------------------------------------------- data.rs:54-88 splits ----
+// SipHash-2-4 (Aumasson & Bernstein) of one 8-byte little-endian word: what siphasher's `write_usize` + `finish` compute
+static inline uint64_t rotl64(uint64_t x, int b) { return (x << b) | (x >> (64 - b)); }
+static uint64_t siphash24_u64(uint64_t k0, uint64_t k1, uint64_t m) {
+    uint64_t v0 = k0 ^ 0x736f6d6570736575ULL, v1 = k1 ^ 0x646f72616e646f6dULL, v2 = k0 ^ 0x6c7967656e657261ULL, v3 = k1 ^ 0x7465646279746573ULL;
+    auto round = [&]() {
+        v0 += v1; v1 = rotl64(v1, 13); v1 ^= v0; v0 = rotl64(v0, 32);
+        v2 += v3; v3 = rotl64(v3, 16); v3 ^= v2;
+        v0 += v3; v3 = rotl64(v3, 21); v3 ^= v0;
+        v2 += v1; v1 = rotl64(v1, 17); v1 ^= v2; v2 = rotl64(v2, 32);
+    };
+    v3 ^= m; round(); round(); v0 ^= m;
+    const uint64_t b = (uint64_t)8 << 56;          // total length 8 bytes, no tail bytes
+    v3 ^= b; round(); round(); v0 ^= b;
+    v2 ^= 0xff; round(); round(); round(); round();
+    return v0 ^ v1 ^ v2 ^ v3;
+}
+// data.rs:69-88 user_based_split: is_train(x) = siphash(key_0, key_1, user) % 100_000 > (test_fraction * 100_000) as u64,
+// the keys being two Uniform<u64>[0, MAX) draws from the caller's rng.  Host-only (data preparation of the tests / examples).
+sbr_status sbr_user_based_split(const uint64_t* user_ids, size_t nnz, uint32_t rng_state[4], float test_fraction, uint8_t* out_is_train) {
+    if ((nnz && (!user_ids || !out_is_train)) || !rng_state) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if ((rng_state[0] | rng_state[1] | rng_state[2] | rng_state[3]) == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "xorshift state must not be all zero");
+    XorShift rng; rng.x = rng_state[0]; rng.y = rng_state[1]; rng.z = rng_state[2]; rng.w = rng_state[3];
+    const uint64_t denominator = 100000;
+    const uint64_t cutoff = (uint64_t)(test_fraction * (float)denominator);
+    const uint64_t k0 = xs_gen_below(rng, UINT64_MAX), k1 = xs_gen_below(rng, UINT64_MAX);
+    for (size_t i = 0; i < nnz; ++i) out_is_train[i] = (siphash24_u64(k0, k1, user_ids[i]) % denominator) > cutoff;
+    rng_state[0] = rng.x; rng_state[1] = rng.y; rng_state[2] = rng.z; rng_state[3] = rng.w;
+    return SBR_OK;
+}
+// data.rs:54-64 train_test_split: interactions.shuffle(rng) (Fisher-Yates from the top), then the FIRST
+// (test_fraction * len) as usize shuffled interactions are the test set.  perm[k] = original index of the k-th
+// shuffled interaction; perm[0 .. *num_test) is test, the rest is train.
+sbr_status sbr_train_test_split(size_t nnz, uint32_t rng_state[4], float test_fraction, uint64_t* perm, size_t* num_test) {
+    if ((nnz && !perm) || !rng_state || !num_test) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if ((rng_state[0] | rng_state[1] | rng_state[2] | rng_state[3]) == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "xorshift state must not be all zero");
+    XorShift rng; rng.x = rng_state[0]; rng.y = rng_state[1]; rng.z = rng_state[2]; rng.w = rng_state[3];
+    for (size_t i = 0; i < nnz; ++i) perm[i] = i;
+    for (size_t i = nnz; i >= 2;) { i -= 1; const size_t j = (size_t)xs_gen_below(rng, (uint64_t)i + 1); std::swap(perm[i], perm[j]); }
+    *num_test = (size_t)(test_fraction * (float)nnz);
+    rng_state[0] = rng.x; rng_state[1] = rng.y; rng_state[2] = rng.z; rng_state[3] = rng.w;
+    return SBR_OK;
+}
+
 // host-only view of the schedule that fit() builds (no device needed): lets CPU-only CI pin the chunker / filter /
 // master shuffle against the oracle
 sbr_status sbr_host_schedule(const sbr_compressed* c, size_t max_sequence_length, uint32_t rng_state[4], uint64_t* starts, uint32_t* lens,

@@ -162,3 +162,30 @@ def test_host_schedule_empty_is_no_interactions(pkg):
     data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=10)
     with pytest.raises(pkg.NoInteractions):                # FittingError::NoInteractions (sequence_model.rs:86-88)
         data.host_schedule(8, (1, 2, 3, 4))
+
+
+def test_user_based_split_equals_oracle_and_reference_recipe(pkg, oracle, ml100k):
+    """data.rs:69-88 in the library (own SipHash-2-4) against the oracle's restatement at the reference's own test
+    recipe: seed [42;16], test fraction 0.2 (lstm.rs:428-430); identical mask, identical rng state afterwards; no user
+    on both sides."""
+    up = ml100k["user_ptr"].astype(np.int64)
+    users = np.repeat(np.arange(944), np.diff(up)).astype(np.uint64)
+    r = oracle.make_rng(bytes([42] * 16))
+    mask, state = pkg.user_based_split(users, (r.x, r.y, r.z, r.w), 0.2)
+    omask, r2 = oracle.user_based_split(users, bytes([42] * 16), 0.2)
+    assert np.array_equal(mask, omask) and state == (r2.x, r2.y, r2.z, r2.w)
+    train_users, test_users = set(users[mask].tolist()), set(users[~mask].tolist())
+    assert not (train_users & test_users) and 0.12 < len(test_users) / 943 < 0.28
+
+
+def test_train_test_split_is_the_reference_shuffle(pkg, oracle):
+    """data.rs:54-64: Fisher-Yates shuffle with the caller's rng, the first (fraction * len) as usize are the test set."""
+    import ctypes as C
+    n = 1000
+    r = oracle.make_rng(bytes(range(16)))
+    train, test, state = pkg.train_test_split(n, (r.x, r.y, r.z, r.w), 0.25)
+    operm = np.arange(n, dtype=np.uint32)
+    oracle.lib().sbo_shuffle_u32(C.byref(r), operm.ctypes.data_as(oracle.u32p), n)
+    assert len(test) == 250 and len(train) == 750
+    assert np.array_equal(np.concatenate([test, train]).astype(np.uint32), operm) and state == (r.x, r.y, r.z, r.w)
+    assert sorted(np.concatenate([train, test]).tolist()) == list(range(n))
