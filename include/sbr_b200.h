@@ -85,6 +85,15 @@ sbr_status sbr_compressed_user_chunks(const sbr_compressed* c, size_t user_id, s
 sbr_status sbr_compressed_upload(sbr_compressed* c);
 void sbr_compressed_free(sbr_compressed* c);
 
+/* data.rs:69-88 user_based_split (no user in both sets): out_is_train[i] = SipHash-2-4(key_0, key_1, user_ids[i]) % 100000 >
+ * (test_fraction * 100000) as u64, key_0 / key_1 = two Uniform<u64> draws from the xorshift128 state `rng_state` (in / out).
+ * Host-only: data preparation of the reference's tests and examples (lstm.rs:428-430). */
+sbr_status sbr_user_based_split(const uint64_t* user_ids, size_t nnz, uint32_t rng_state[4], float test_fraction,
+                                uint8_t* out_is_train);
+/* data.rs:54-64 train_test_split: shuffle, then the first (test_fraction * nnz) as usize shuffled interactions are the
+ * test set.  perm[k] = original index of the k-th shuffled interaction; perm[0 .. *num_test) is test, the rest train. */
+sbr_status sbr_train_test_split(size_t nnz, uint32_t rng_state[4], float test_fraction, uint64_t* perm, size_t* num_test);
+
 /* ------------------------------------------------- lstm.rs:54-202 / ewma.rs:59-206 ------------------------ */
 sbr_hyperparameters* sbr_lstm_hyperparameters_new(size_t num_items, size_t max_sequence_length); /* lstm.rs:56-71 */
 sbr_hyperparameters* sbr_ewma_hyperparameters_new(size_t num_items, size_t max_sequence_length); /* ewma.rs:61-76 */
@@ -136,7 +145,13 @@ sbr_status sbr_model_set_rng_state(sbr_model* m, const uint32_t state[4]);
 void sbr_model_free(sbr_model* m);
 
 /* ------------------------------------------------ multi-GPU (one process per GPU) ------------------------- */
-/* The reference shares ONE parameter set between its worker threads (Arc<HogwildParameter>, lstm.rs:175-181).  Across
+/* Three ways to use several GPUs.  (i) Small catalogues: build an ordinary model per rank, fit each
+ * rank's users, and between fits sum the deltas of every parameter / optimizer-state blob over the ranks
+ * (sbr_model_get_parameter -> all-reduce -> sbr_model_set_parameter; bench.py's ReplicaSync) -- needs nothing below.
+ * (ii) One shared model over NVLink peer mappings (sbr_hyper_shard + sbr_model_ipc_*), described next.
+ * (iii) Catalogues too large for one GPU: row-sharded table with an explicit NCCL exchange (sbr_dist_*).
+ *
+ * (ii) The reference shares ONE parameter set between its worker threads (Arc<HogwildParameter>, lstm.rs:175-181).  Across
  * GPUs the same is done over NVLink: the item table, biases and their optimizer state are row-sharded (item_id %
  * world) and every rank's training kernel gathers / updates remote rows directly in the owner's HBM through CUDA-IPC
  * peer mappings (no staging copies, no collective on the data path); the small dense parameters live on rank 0.
@@ -169,15 +184,6 @@ typedef struct {
     double total_device_ms;  /* CUDA-event time from first H2D to last D2H */
     double host_prepare_ms;  /* sub-sequence build + shuffle + partitioning on the host */
 } sbr_fit_stats;
-
-/* data.rs:69-88 user_based_split (no user in both sets): out_is_train[i] = SipHash-2-4(key_0, key_1, user_ids[i]) % 100000 >
- * (test_fraction * 100000) as u64, key_0 / key_1 = two Uniform<u64> draws from the xorshift128 state `rng_state` (in / out).
- * Host-only: data preparation of the reference's tests and examples (lstm.rs:428-430). */
-sbr_status sbr_user_based_split(const uint64_t* user_ids, size_t nnz, uint32_t rng_state[4], float test_fraction,
-                                uint8_t* out_is_train);
-/* data.rs:54-64 train_test_split: shuffle, then the first (test_fraction * nnz) as usize shuffled interactions are the
- * test set.  perm[k] = original index of the k-th shuffled interaction; perm[0 .. *num_test) is test, the rest train. */
-sbr_status sbr_train_test_split(size_t nnz, uint32_t rng_state[4], float test_fraction, uint64_t* perm, size_t* num_test);
 
 /* Host-only test hook: the schedule fit() builds from a CSR -- sequence_model.rs:76-84: chunks of every user
  * (data.rs:406-432), the len > 2 filter (:81) and the master-rng shuffle (:84).  Needs no device.  `rng_state` is the
