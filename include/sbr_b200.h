@@ -128,6 +128,10 @@ sbr_status sbr_model_predict(const sbr_model* m, const float* user, const uint64
 sbr_status sbr_model_mrr_score(const sbr_model* m, const sbr_compressed* test, float* out);
 /* ParameterNode::index (lstm.rs:272-283): bit-exact row gather, out is [n, embedding_dim] */
 sbr_status sbr_model_gather_rows(const sbr_model* m, const uint64_t* item_ids, size_t n, float* out);
+/* the same gather timed on the device (CUDA events around 1 warm-up + `iters` launches; *kernel_ms = mean per launch):
+ * the "embed-gather HBM GB/s" of BASELINE.json; algorithmic bytes per row 4 D + 4 D + 4.  `out` may be NULL. */
+sbr_status sbr_model_gather_rows_timed(const sbr_model* m, const uint64_t* item_ids, size_t n, float* out, int iters,
+                                       double* kernel_ms);
 
 size_t sbr_model_embedding_dim(const sbr_model* m);
 size_t sbr_model_num_items(const sbr_model* m);

@@ -39,7 +39,7 @@ EXPORTS = [
     "sbr_hyper_num_threads", "sbr_hyper_parallelism", "sbr_hyper_from_seed", "sbr_hyper_optimizer", "sbr_hyper_free",
     "sbr_hyper_build",
     "sbr_model_fit", "sbr_model_user_representation", "sbr_model_user_representations", "sbr_model_predict",
-    "sbr_model_mrr_score", "sbr_model_gather_rows", "sbr_model_embedding_dim", "sbr_model_num_items",
+    "sbr_model_mrr_score", "sbr_model_gather_rows", "sbr_model_gather_rows_timed", "sbr_model_embedding_dim", "sbr_model_num_items",
     "sbr_model_parameter_len", "sbr_model_get_parameter", "sbr_model_set_parameter", "sbr_model_get_num_updates",
     "sbr_model_set_num_updates", "sbr_model_get_rng_state", "sbr_model_set_rng_state", "sbr_model_free",
     "sbr_hyper_shard", "sbr_hyper_virtual_shards", "sbr_model_ipc_handle_size", "sbr_model_ipc_export",
@@ -132,6 +132,7 @@ def lib():
     L.sbr_model_predict.argtypes = [vp, f32p, u64p, C.c_size_t, f32p]
     L.sbr_model_mrr_score.argtypes = [vp, vp, f32p]
     L.sbr_model_gather_rows.argtypes = [vp, u64p, C.c_size_t, f32p]
+    L.sbr_model_gather_rows_timed.argtypes = [vp, u64p, C.c_size_t, f32p, C.c_int, C.POINTER(C.c_double)]
     L.sbr_model_embedding_dim.restype = C.c_size_t
     L.sbr_model_embedding_dim.argtypes = [vp]
     L.sbr_model_num_items.restype = C.c_size_t
@@ -525,6 +526,13 @@ class _Model:
         out = np.zeros((len(ids), self.embedding_dim), dtype=np.float32)
         _check(lib().sbr_model_gather_rows(self._m, _p(ids, u64p), len(ids), _p(out, f32p)))
         return out
+
+    def gather_rows_timed(self, item_ids, iters=5):
+        """mean device time (ms) of the stand-alone gather kernel over `iters` launches (sbr_model_gather_rows_timed)"""
+        ids = _u64(item_ids)
+        ms = C.c_double()
+        _check(lib().sbr_model_gather_rows_timed(self._m, _p(ids, u64p), len(ids), None, int(iters), C.byref(ms)))
+        return ms.value
 
     def get_parameter(self, name):
         n = C.c_size_t()

@@ -1139,6 +1139,47 @@ sbr_status sbr_model_mrr_score(const sbr_model* m, const sbr_compressed* test, f
     return SBR_OK;
 }
 
+// Stand-alone embedding gather timed on the device (BASELINE.json metric "embed-gather HBM GB/s"): the ids are uploaded
+// once, gather_rows_kernel runs 1 + iters times on the model's stream between CUDA events, *kernel_ms is the mean of the
+// timed launches.  Algorithmic bytes per row: 4 D read + 4 D written + 4 (u32 id).  `out` may be NULL (nothing copied back).
+sbr_status sbr_model_gather_rows_timed(const sbr_model* m, const uint64_t* item_ids, size_t n, float* out, int iters, double* kernel_ms) {
+    if (!m || !kernel_ms || iters < 1 || (n && !item_ids)) return fail(SBR_ERR_INVALID_ARGUMENT, "bad argument");
+    if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before using it");
+    sbr_status s = require_device();
+    if (s) return s;
+    *kernel_ms = 0.0;
+    if (n == 0) return SBR_OK;
+    std::lock_guard<std::mutex> lk(m->mu);
+    cudaStream_t st = m->stream;
+    const size_t D = m->dev.D;
+    uint32_t* d_ids = nullptr; float* d_out = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CU(cudaMalloc(&d_ids, n * sizeof(uint32_t)));
+    cudaError_t e = cudaMalloc(&d_out, n * D * sizeof(float));
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) {
+        s = upload_ids_u32(item_ids, n, d_ids, st, m->dev.N, nullptr);
+        if (s == SBR_OK) {
+            e = launch_gather_rows(m->dev, d_ids, n, d_out, st);   // warm-up
+            if (e == cudaSuccess) e = cudaEventRecord(e0, st);
+            for (int i = 0; i < iters && e == cudaSuccess; ++i) e = launch_gather_rows(m->dev, d_ids, n, d_out, st);
+            if (e == cudaSuccess) e = cudaEventRecord(e1, st);
+            if (e == cudaSuccess && out) e = cudaMemcpyAsync(out, d_out, n * D * sizeof(float), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            float ms = 0.0f;
+            if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+            *kernel_ms = (double)ms / iters;
+        }
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(d_ids); cudaFree(d_out);
+    if (s) return s;
+    if (e != cudaSuccess) return cuda_fail(e, "gather_rows_timed");
+    return SBR_OK;
+}
+
 sbr_status sbr_model_gather_rows(const sbr_model* m, const uint64_t* item_ids, size_t n, float* out) {
     if (!m || (n && (!item_ids || !out))) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before using it");
