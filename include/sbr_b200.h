@@ -109,6 +109,28 @@ sbr_status sbr_hyper_num_threads(sbr_hyperparameters* h, size_t v);
 sbr_status sbr_hyper_parallelism(sbr_hyperparameters* h, sbr_parallelism v); /* lstm.rs:116-119 */
 sbr_status sbr_hyper_from_seed(sbr_hyperparameters* h, const uint8_t seed[16]); /* lstm.rs:129-132 */
 sbr_status sbr_hyper_optimizer(sbr_hyperparameters* h, sbr_optimizer v);  /* lstm.rs:135-138 */
+/* Hyperparameters::random(num_items, rng) (lstm.rs:141-172 / ewma.rs:139-170), "useful for hyperparameter search":
+ * draws, in the reference's field order, max_sequence_length = 2^U[4,8), embedding_dim = 2^U[4,8), learning_rate =
+ * 10^U[-3,0.5), l2_penalty = 10^U[-7,-3), loss in {BPR, Hinge}, optimizer in {Adam, Adagrad}, (LSTM: variant in {Normal,
+ * Coupled},) parallelism, num_threads = U[1, host threads + 1), num_epochs = 2^U[3,7) from the xorshift128 state
+ * `rng_state` (in / out; rand 0.5 Uniform sampling [rand-recalled]); the model seed comes from the clock like
+ * thread_rng() at lstm.rs:167.  Returns NULL on a bad argument. */
+sbr_hyperparameters* sbr_lstm_hyperparameters_random(size_t num_items, uint32_t rng_state[4]);
+sbr_hyperparameters* sbr_ewma_hyperparameters_random(size_t num_items, uint32_t rng_state[4]);
+/* Engine knob without a reference analogue: 1 = never use the tf32 / bf16 tensor-core tile kernel, i.e. exact fp32
+ * arithmetic on every path (the tile kernel is the default for LSTM dim 32 with >= 128 partitions). */
+sbr_status sbr_hyper_exact_arithmetic(sbr_hyperparameters* h, int on);
+/* The public fields of Hyperparameters (lstm.rs:39-52) as plain data: what a serde round trip / a Rust shim reads. */
+typedef struct {
+    int32_t model;            /* 0 LSTM, 1 EWMA */
+    int32_t lstm_variant, loss, optimizer, parallelism;
+    int32_t exact_arithmetic;
+    uint64_t num_items, max_sequence_length, embedding_dim, num_threads, num_epochs;
+    float learning_rate, l2_penalty;
+    uint8_t seed[16];
+} sbr_hyper_values;
+sbr_status sbr_hyper_get_values(const sbr_hyperparameters* h, sbr_hyper_values* out);
+sbr_status sbr_model_get_hyper_values(const sbr_model* m, sbr_hyper_values* out);
 void sbr_hyper_free(sbr_hyperparameters* h);
 /* Hyperparameters::build(self) (lstm.rs:197-201 / ewma.rs:201-205): consumes `h` (also on failure). */
 sbr_status sbr_hyper_build(sbr_hyperparameters* h, sbr_model** out);
@@ -146,6 +168,20 @@ sbr_status sbr_model_set_num_updates(sbr_model* m, uint64_t v);
 /* Hyperparameters.rng (lstm.rs:49, serialised with the model): xorshift128 state x,y,z,w */
 sbr_status sbr_model_get_rng_state(const sbr_model* m, uint32_t out[4]);
 sbr_status sbr_model_set_rng_state(sbr_model* m, const uint32_t state[4]);
+/* Checkpoint (the reference derives Serialize / Deserialize for the whole model incl. hyperparameters, rng and the
+ * optimizer state inside HogwildParameter: lstm.rs:38-52,204-210,386-389).  ONE flat little-endian file, layout:
+ *   0   char[8]  "SBRB200\0"          8   u32 version (1)        12  u32 header_bytes (offset of the first blob)
+ *   16  sbr_hyper_values (88 bytes, the struct above)
+ *   104 u32[4] xorshift128 state of Hyperparameters.rng           120 u64 num_updates (Adam step counter)
+ *   128 u32 n_blobs, u32 pad, then n_blobs x { char name[32]; u64 len_floats; u64 file_offset }
+ *   header_bytes.. the blobs as raw f32: "item_embeddings" [N*D], "item_biases" [N], "lstm_weights" [2D*4D] +
+ *   "lstm_biases" [4D] (LSTM) or "alpha" [D] (EWMA), each followed by its ".s1" (and ".s2" for Adam) state blob.
+ * save reads the device tables (a row-sharded model must be attached); load builds a new single-GPU model on the
+ * selected device; restore overwrites the parameters of an existing model of the same shape (every rank of a sharded
+ * model restores its own rows).  A restored model continues bit-for-bit (tests/test_gpu_checkpoint.py). */
+sbr_status sbr_model_save(const sbr_model* m, const char* path);
+sbr_status sbr_model_load(const char* path, sbr_model** out);
+sbr_status sbr_model_restore(sbr_model* m, const char* path);
 void sbr_model_free(sbr_model* m);
 
 /* ------------------------------------------------ multi-GPU (one process per GPU) ------------------------- */

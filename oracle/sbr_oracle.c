@@ -315,8 +315,55 @@ static void adam_coeffs(const sbo_model* m, uint64_t t, float* c1, float* c2) {
     if (m->h.optimizer == SBO_OPT_ADAM) { *c1 = 1.0f - powf(0.9f, (float)t); *c2 = 1.0f - powf(0.999f, (float)t); }
 }
 
+/* Experiment switch (profiles/tools/oracle_mrr_seeds.py --merge): what if wyrm's gradient accumulator SUMS the entries
+ * of a row that is recorded several times in one step (a dense-shaped gradient buffer plus a set of touched rows) and
+ * the optimizer visits every touched row once, in ascending row order?  The source is not on this box; the default (0)
+ * is the un-merged list the survey recalled.  DESIGN.md 5 reports what the MRR floors say about the two readings. */
+static int g_merge_sparse = 0;
+void sbo_set_merge_sparse(int on) { g_merge_sparse = on; }
+
+static int cmp_u32_idx(const void* a, const void* b) {
+    const uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+    return x < y ? -1 : x > y;
+}
+static void apply_sparse_merged(sbo_model* m, const sbo_ws* w, float c1, float c2) {
+    const size_t D = m->D; const float lr = m->h.learning_rate, l2 = m->h.l2_penalty;
+    const int adam = m->h.optimizer == SBO_OPT_ADAM;
+    uint64_t* key = (uint64_t*)malloc(sizeof(uint64_t) * (w->nrows + w->nbrows + 1));
+    float* acc = (float*)malloc(sizeof(float) * D);
+    for (size_t e = 0; e < w->nrows; ++e) key[e] = ((uint64_t)w->rows[e] << 32) | e;   /* (row, recording order) */
+    qsort(key, w->nrows, sizeof(uint64_t), cmp_u32_idx);
+    for (size_t a = 0; a < w->nrows;) {
+        const size_t r = (size_t)(key[a] >> 32);
+        memset(acc, 0, sizeof(float) * D);
+        size_t b = a;
+        for (; b < w->nrows && (size_t)(key[b] >> 32) == r; ++b) {
+            const float* g = w->grads + (size_t)(key[b] & 0xffffffffu) * D;
+            for (size_t d = 0; d < D; ++d) acc[d] += g[d];
+        }
+        float* wv = m->E + r * D; float* s1 = m->E_s1 + r * D; float* s2 = m->E_s2 + r * D;
+        for (size_t d = 0; d < D; ++d) {
+            if (adam) adam_elem(wv + d, s1 + d, s2 + d, acc[d], lr, l2, c1, c2);
+            else adagrad_elem(wv + d, s1 + d, acc[d], lr, l2);
+        }
+        a = b;
+    }
+    for (size_t e = 0; e < w->nbrows; ++e) key[e] = ((uint64_t)w->brows[e] << 32) | e;
+    qsort(key, w->nbrows, sizeof(uint64_t), cmp_u32_idx);
+    for (size_t a = 0; a < w->nbrows;) {
+        const size_t r = (size_t)(key[a] >> 32);
+        float g = 0.0f; size_t b = a;
+        for (; b < w->nbrows && (size_t)(key[b] >> 32) == r; ++b) g += w->bgrads[key[b] & 0xffffffffu];
+        if (adam) adam_elem(m->b + r, m->b_s1 + r, m->b_s2 + r, g, lr, l2, c1, c2);
+        else adagrad_elem(m->b + r, m->b_s1 + r, g, lr, l2);
+        a = b;
+    }
+    free(key); free(acc);
+}
+
 /* sparse rows: one update per recorded (row, grad) entry, in order, duplicates NOT merged [wyrm-recalled] */
 static void apply_sparse(sbo_model* m, const sbo_ws* w, float c1, float c2) {
+    if (g_merge_sparse) { apply_sparse_merged(m, w, c1, c2); return; }
     const size_t D = m->D; const float lr = m->h.learning_rate, l2 = m->h.l2_penalty;
     const int adam = m->h.optimizer == SBO_OPT_ADAM;
     for (size_t e = 0; e < w->nrows; ++e) {

@@ -50,6 +50,8 @@ void     sbo_shuffle_u32(sbo_rng* r, uint32_t* v, size_t n);             /* Rng:
 
 /* counter-based negative draw shared bit-for-bit with the CUDA engine */
 uint32_t sbo_draw_item(uint64_t key, uint64_t step, uint32_t t, uint32_t j, uint32_t num_items);
+/* experiment switch: 1 = sum the entries of a row recorded several times in one step, one optimizer visit per row */
+void sbo_set_merge_sparse(int on);
 
 /* ---- data.rs ---- */
 /* data.rs:236-265: stable sort by (user, timestamp), histogram, prefix sum. Outputs caller-allocated. */

@@ -37,7 +37,8 @@ EXPORTS = [
     "sbr_lstm_hyperparameters_new", "sbr_ewma_hyperparameters_new", "sbr_hyper_learning_rate", "sbr_hyper_l2_penalty",
     "sbr_hyper_embedding_dim", "sbr_hyper_num_epochs", "sbr_hyper_loss", "sbr_hyper_lstm_variant",
     "sbr_hyper_num_threads", "sbr_hyper_parallelism", "sbr_hyper_from_seed", "sbr_hyper_optimizer", "sbr_hyper_free",
-    "sbr_hyper_build",
+    "sbr_hyper_build", "sbr_lstm_hyperparameters_random", "sbr_ewma_hyperparameters_random", "sbr_hyper_exact_arithmetic",
+    "sbr_hyper_get_values", "sbr_model_get_hyper_values", "sbr_model_save", "sbr_model_load", "sbr_model_restore",
     "sbr_model_fit", "sbr_model_user_representation", "sbr_model_user_representations", "sbr_model_predict",
     "sbr_model_mrr_score", "sbr_model_gather_rows", "sbr_model_gather_rows_timed", "sbr_model_embedding_dim", "sbr_model_num_items",
     "sbr_model_parameter_len", "sbr_model_get_parameter", "sbr_model_set_parameter", "sbr_model_get_num_updates",
@@ -46,6 +47,22 @@ EXPORTS = [
     "sbr_model_ipc_attach", "sbr_dist_unique_id", "sbr_dist_init", "sbr_dist_finalize",
     "sbr_fit_plan_create", "sbr_fit_plan_run", "sbr_fit_plan_stats", "sbr_fit_plan_free", "sbr_model_last_fit_stats",
 ]
+
+
+class HyperValues(C.Structure):
+    """sbr_hyper_values: the public fields of Hyperparameters (lstm.rs:39-52) as plain data"""
+    _fields_ = [
+        ("model", C.c_int32), ("lstm_variant", C.c_int32), ("loss", C.c_int32), ("optimizer", C.c_int32),
+        ("parallelism", C.c_int32), ("exact_arithmetic", C.c_int32),
+        ("num_items", C.c_uint64), ("max_sequence_length", C.c_uint64), ("embedding_dim", C.c_uint64),
+        ("num_threads", C.c_uint64), ("num_epochs", C.c_uint64),
+        ("learning_rate", C.c_float), ("l2_penalty", C.c_float), ("seed", C.c_uint8 * 16),
+    ]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "seed"}
+        d["seed"] = bytes(self.seed)
+        return d
 
 
 class FitStats(C.Structure):
@@ -126,6 +143,15 @@ def lib():
     L.sbr_hyper_optimizer.argtypes = [vp, C.c_int]
     L.sbr_hyper_free.argtypes = [vp]
     L.sbr_hyper_build.argtypes = [vp, C.POINTER(vp)]
+    for f in ("sbr_lstm_hyperparameters_random", "sbr_ewma_hyperparameters_random"):
+        getattr(L, f).restype = vp
+        getattr(L, f).argtypes = [C.c_size_t, C.POINTER(C.c_uint32)]
+    L.sbr_hyper_exact_arithmetic.argtypes = [vp, C.c_int]
+    L.sbr_hyper_get_values.argtypes = [vp, C.POINTER(HyperValues)]
+    L.sbr_model_get_hyper_values.argtypes = [vp, C.POINTER(HyperValues)]
+    L.sbr_model_save.argtypes = [vp, C.c_char_p]
+    L.sbr_model_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.sbr_model_restore.argtypes = [vp, C.c_char_p]
     L.sbr_model_fit.argtypes = [vp, vp, f32p]
     L.sbr_model_user_representation.argtypes = [vp, u64p, C.c_size_t, f32p]
     L.sbr_model_user_representations.argtypes = [vp, u64p, u64p, C.c_size_t, f32p]
@@ -339,7 +365,8 @@ class CompressedInteractions:
         up, ii, tt = u64p(), u64p(), u64p()
         _check(lib().sbr_compressed_borrow(self._h, C.byref(up), C.byref(ii), C.byref(tt)))
         nu, nnz = self.num_users(), len(self)
-        f = lambda p, n: np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0, dtype=np.uint64)
+        # a NULL pointer (a CSR borrowed without timestamps) reads as zeros, like sbr_compressed_from_csr(timestamps=NULL)
+        f = lambda p, n: np.ctypeslib.as_array(p, shape=(n,)).copy() if (n and p) else np.zeros(n, dtype=np.uint64)
         return f(up, nu + 1), f(ii, nnz), f(tt, nnz)
 
     def to_interactions(self):
@@ -424,6 +451,27 @@ class _Hyperparameters:
         self._h = C.c_void_p(new(num_items, max_sequence_length))
         if not self._h:
             raise MemoryError()
+
+    @classmethod
+    def random(cls, num_items, rng_state):
+        """Hyperparameters::random(num_items, rng) (lstm.rs:141-172): returns (hyperparameters, advanced rng state)."""
+        fn = lib().sbr_lstm_hyperparameters_random if cls._KIND == "lstm" else lib().sbr_ewma_hyperparameters_random
+        st = (C.c_uint32 * 4)(*rng_state)
+        h = fn(num_items, st)
+        if not h:
+            raise SbrError(SBR_ERR_INVALID_ARGUMENT, lib().sbr_last_error_string().decode())
+        self = cls.__new__(cls)
+        self._h = C.c_void_p(h)
+        return self, tuple(st)
+
+    def values(self):
+        v = HyperValues()
+        _check(lib().sbr_hyper_get_values(self._h, C.byref(v)))
+        return v.as_dict()
+
+    def exact_arithmetic(self, on=True):
+        """engine knob: keep exact fp32 arithmetic (never the tf32 / bf16 tensor-core tile kernel)"""
+        return self._set("sbr_hyper_exact_arithmetic", int(bool(on)))
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:
@@ -566,49 +614,18 @@ class _Model:
         st = (C.c_uint32 * 4)(*v)
         _check(lib().sbr_model_set_rng_state(self._m, st))
 
-    # -- checkpoint (the reference derives Serialize/Deserialize for the whole model -- parameters,
-    #    optimizer state inside HogwildParameter, the hyper-parameter rng; lstm.rs:204-210,386-389).  The flat-file form
-    #    here is an .npz of the canonical host-order blobs: every parameter, its optimizer-state slots, the master
-    #    xorshift state and the update counter.  load_state() into a model built from the same hyper-parameters
-    #    continues training exactly where the saved one stopped (optimizer state persists across fit calls, 5. in SURVEY).
-    def parameter_names(self):
-        names = ["item_embeddings", "item_biases"]
-        for extra in ("lstm_weights", "lstm_biases", "alpha"):
-            n = C.c_size_t()
-            if lib().sbr_model_parameter_len(self._m, extra.encode(), C.byref(n)) == 0:
-                names.append(extra)
-        return names
+    # -- checkpoint: written and read by the C library (sbr_model_save / load / restore; layout in include/sbr_b200.h) --
+    def hyper_values(self):
+        v = HyperValues()
+        _check(lib().sbr_model_get_hyper_values(self._m, C.byref(v)))
+        return v.as_dict()
 
-    def state_dict(self):
-        out = {}
-        for n in self.parameter_names():
-            out[n] = self.get_parameter(n)
-            for slot in (".s1", ".s2"):
-                k = C.c_size_t()
-                if lib().sbr_model_parameter_len(self._m, (n + slot).encode(), C.byref(k)) == 0:
-                    try:
-                        out[n + slot] = self.get_parameter(n + slot)
-                    except SbrError:
-                        pass
-        out["rng_state"] = np.asarray(self.rng_state, dtype=np.uint32)
-        out["num_updates"] = np.asarray([self.num_updates], dtype=np.uint64)
-        return out
+    def save(self, path):
+        _check(lib().sbr_model_save(self._m, os.fsencode(path)))
 
-    def load_state_dict(self, state):
-        for k, v in state.items():
-            if k == "rng_state":
-                self.rng_state = tuple(int(x) for x in v)
-            elif k == "num_updates":
-                self.num_updates = int(np.asarray(v).ravel()[0])
-            else:
-                self.set_parameter(k, v)
-
-    def save_state(self, path):
-        np.savez(path, **self.state_dict())
-
-    def load_state(self, path):
-        with np.load(path) as z:
-            self.load_state_dict({k: z[k] for k in z.files})
+    def restore(self, path):
+        """overwrite parameters, optimizer state, rng and update counter from a checkpoint of the same shape"""
+        _check(lib().sbr_model_restore(self._m, os.fsencode(path)))
 
     def ipc_export(self):
         buf = C.create_string_buffer(lib().sbr_model_ipc_handle_size())
@@ -685,6 +702,15 @@ class lstm:  # namespace mirror of sbr::models::lstm
 class ewma:  # namespace mirror of sbr::models::ewma
     Hyperparameters = _EwmaHyperparameters
     ImplicitEWMAModel = ImplicitEWMAModel
+
+
+def load_model(path):
+    """sbr_model_load: a new model (hyperparameters included) from a checkpoint written by Model.save()"""
+    m = C.c_void_p()
+    _check(lib().sbr_model_load(os.fsencode(path), C.byref(m)))
+    v = HyperValues()
+    _check(lib().sbr_model_get_hyper_values(m, C.byref(v)))
+    return (ImplicitLSTMModel if v.model == 0 else ImplicitEWMAModel)(m)
 
 
 def mrr_score(model, test):

@@ -81,22 +81,25 @@ sbr_status cuda_fail(cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #expr);         \
     } while (0)
 
-struct DeviceInfo { bool ok = false; int sms = 0; std::string why; };
+struct DeviceInfo { bool ok = false; int sms = 0; int device = -1; std::string why; };
 
+// properties of the CURRENTLY selected device (re-queried whenever sbr_set_device picked another one)
 DeviceInfo& device_info() {
     static DeviceInfo info;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        int n = 0;
-        cudaError_t e = cudaGetDeviceCount(&n);
-        if (e != cudaSuccess || n <= 0) { info.why = "no CUDA device available (this library has no CPU fallback)"; cudaGetLastError(); return; }
-        if (g_device >= n) { info.why = "selected device index out of range"; return; }
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, g_device) != cudaSuccess) { info.why = "cudaGetDeviceProperties failed"; return; }
-        if (p.major != 10) { info.why = "device is not sm_100 (B200): kernels are built for sm_100a only"; return; }
-        info.sms = p.multiProcessorCount;
-        info.ok = true;
-    });
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (info.device == g_device) return info;
+    info = DeviceInfo();
+    info.device = g_device;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { info.why = "no CUDA device available (this library has no CPU fallback)"; cudaGetLastError(); return info; }
+    if (g_device >= n) { info.why = "selected device index out of range"; return info; }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, g_device) != cudaSuccess) { info.why = "cudaGetDeviceProperties failed"; return info; }
+    if (p.major != 10) { info.why = "device is not sm_100 (B200): kernels are built for sm_100a only"; return info; }
+    info.sms = p.multiProcessorCount;
+    info.ok = true;
     return info;
 }
 
@@ -243,6 +246,7 @@ struct sbr_hyperparameters {
     size_t num_epochs = 10;                                              // lstm.rs:69
     int shard_rank = 0, shard_world = 1;   // one process per GPU: this rank owns rows with id % world == rank
     int virtual_shards = 1;                // > 1: shard the table inside this process (exercises the sharded addressing)
+    int exact = 0;                         // sbr_hyper_exact_arithmetic
 };
 
 struct sbr_model {
@@ -567,6 +571,11 @@ sbr_status sbr_hyper_lstm_variant(sbr_hyperparameters* h, sbr_lstm_variant v) {
     h->lstm_variant = v;
     return SBR_OK;
 }
+sbr_status sbr_hyper_exact_arithmetic(sbr_hyperparameters* h, int on) {
+    if (!h) return fail(SBR_ERR_INVALID_ARGUMENT, "null hyperparameters");
+    h->exact = on != 0;
+    return SBR_OK;
+}
 sbr_status sbr_hyper_from_seed(sbr_hyperparameters* h, const uint8_t seed[16]) {
     if (!h || !seed) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     std::memcpy(h->seed, seed, 16);
@@ -589,8 +598,8 @@ sbr_status sbr_hyper_build(sbr_hyperparameters* hp, sbr_model** out) {
     d.model = h.model; d.variant = h.lstm_variant; d.loss = h.loss; d.opt = h.optimizer;
     d.N = (uint32_t)h.num_items; d.D = (int)h.embedding_dim; d.T = (int)h.max_sequence_length;
     d.S = h.optimizer == SBR_OPTIMIZER_ADAM ? 3 : 2;
-    d.lr = h.learning_rate; d.l2 = h.l2_penalty;
-    d.hbm_resident = (size_t)d.N * d.S * d.D * sizeof(float) > (size_t)96 << 20 && !getenv("SBR_NO_PREFETCH");
+    d.lr = h.learning_rate; d.l2 = h.l2_penalty; d.exact = h.exact;
+    d.hbm_resident = (size_t)d.N * d.S * d.D * sizeof(float) > (size_t)96 << 20;
     d.ndense = h.model == MODEL_LSTM ? (size_t)2 * d.D * 4 * d.D + 4 * d.D : (size_t)d.D;
     const char* why = nullptr;
     if (!train_supported(d, &why)) { delete m; return fail(SBR_ERR_UNSUPPORTED, why); }
@@ -708,7 +717,9 @@ sbr_status sbr_model_ipc_attach(sbr_model* m, const void* all_handles) {
         CU(cudaIpcOpenMemHandle(&pb, hs[3 * g + 1], cudaIpcMemLazyEnablePeerAccess));
         m->dev.Es[g] = static_cast<float*>(pe); m->dev.Bs[g] = static_cast<float4*>(pb);
     }
-    if (r != 0) {  // the dense parameters (LSTM weights / alpha) live on rank 0; everyone updates them Hogwild
+    // Asynchronous: the dense parameters (LSTM weights / alpha) live on rank 0 and everyone updates them Hogwild.
+    // Synchronous: every rank keeps its own replica (identical on all ranks: same all-reduced gradient every round).
+    if (r != 0 && m->h.parallelism != SBR_PARALLELISM_SYNCHRONOUS) {
         void* pd = nullptr;
         CU(cudaIpcOpenMemHandle(&pd, hs[2], cudaIpcMemLazyEnablePeerAccess));
         m->dev.dense = static_cast<float*>(pd);
@@ -788,6 +799,183 @@ sbr_status sbr_model_set_rng_state(sbr_model* m, const uint32_t state[4]) {
     if (!m || !state) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if ((state[0] | state[1] | state[2] | state[3]) == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "xorshift state must not be all zero");
     m->rng.x = state[0]; m->rng.y = state[1]; m->rng.z = state[2]; m->rng.w = state[3];
+    return SBR_OK;
+}
+
+// ------------------------------------------------------------------------- hyperparameter values / random ----
+static void fill_hyper_values(const sbr_hyperparameters& h, sbr_hyper_values* v) {
+    std::memset(v, 0, sizeof(*v));
+    v->model = h.model; v->lstm_variant = h.lstm_variant; v->loss = h.loss; v->optimizer = h.optimizer;
+    v->parallelism = h.parallelism; v->exact_arithmetic = h.exact;
+    v->num_items = h.num_items; v->max_sequence_length = h.max_sequence_length; v->embedding_dim = h.embedding_dim;
+    v->num_threads = h.num_threads; v->num_epochs = h.num_epochs;
+    v->learning_rate = h.learning_rate; v->l2_penalty = h.l2_penalty;
+    std::memcpy(v->seed, h.seed, 16);
+}
+sbr_status sbr_hyper_get_values(const sbr_hyperparameters* h, sbr_hyper_values* out) {
+    if (!h || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    fill_hyper_values(*h, out);
+    return SBR_OK;
+}
+sbr_status sbr_model_get_hyper_values(const sbr_model* m, sbr_hyper_values* out) {
+    if (!m || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    fill_hyper_values(m->h, out);
+    return SBR_OK;
+}
+
+// rand 0.5 Uniform<f32>::sample [rand-recalled]: value in [1, 2) from the top 23 bits of one u32, then * scale + offset
+static float xs_uniform_f32(XorShift& r, float low, float high) {
+    const float scale = high - low, offset = low - scale;
+    const uint32_t bits = (xs_next_u32(r) >> 9) | 0x3f800000u;
+    float v12; std::memcpy(&v12, &bits, 4);
+    return v12 * scale + offset;
+}
+static sbr_hyperparameters* hyper_random(int model, size_t num_items, uint32_t st[4]) {
+    if (!st || (st[0] | st[1] | st[2] | st[3]) == 0) { g_err = "xorshift state must not be null / all zero"; return nullptr; }
+    sbr_hyperparameters* h = hyper_new(model, num_items, 0);
+    if (!h) return nullptr;
+    XorShift r; r.x = st[0]; r.y = st[1]; r.z = st[2]; r.w = st[3];
+    auto upow2 = [&](uint64_t lo, uint64_t hi) { return (size_t)1 << (lo + xs_gen_below(r, hi - lo)); };   // 2_usize.pow(Uniform::new(lo, hi))
+    auto coin = [&]() { return xs_uniform_f32(r, 0.0f, 1.0f) < 0.5f; };
+    h->max_sequence_length = upow2(4, 8);                                   // lstm.rs:144
+    h->embedding_dim = upow2(4, 8);                                         // :145
+    h->learning_rate = std::pow(10.0f, xs_uniform_f32(r, -3.0f, 0.5f));     // :146
+    h->l2_penalty = std::pow(10.0f, xs_uniform_f32(r, -7.0f, -3.0f));       // :147
+    h->loss = coin() ? SBR_LOSS_BPR : SBR_LOSS_HINGE;                       // :148-152
+    h->optimizer = coin() ? SBR_OPTIMIZER_ADAM : SBR_OPTIMIZER_ADAGRAD;     // :153-157
+    if (model == MODEL_LSTM) h->lstm_variant = coin() ? SBR_LSTM_NORMAL : SBR_LSTM_COUPLED;   // :158-162 (absent in ewma.rs)
+    h->parallelism = coin() ? SBR_PARALLELISM_ASYNCHRONOUS : SBR_PARALLELISM_SYNCHRONOUS;     // :163-167
+    // :168 rng: from thread_rng() -- hyper_new seeded it from the clock
+    const uint64_t host_threads = std::max(1u, std::thread::hardware_concurrency());
+    h->num_threads = 1 + (size_t)xs_gen_below(r, host_threads);            // :169 Uniform::new(1, rayon::current_num_threads() + 1)
+    h->num_epochs = upow2(3, 7);                                            // :170
+    st[0] = r.x; st[1] = r.y; st[2] = r.z; st[3] = r.w;
+    return h;
+}
+sbr_hyperparameters* sbr_lstm_hyperparameters_random(size_t num_items, uint32_t rng_state[4]) { return hyper_random(MODEL_LSTM, num_items, rng_state); }
+sbr_hyperparameters* sbr_ewma_hyperparameters_random(size_t num_items, uint32_t rng_state[4]) { return hyper_random(MODEL_EWMA, num_items, rng_state); }
+
+// ------------------------------------------------------------------------------------------- checkpoint ----
+namespace {
+constexpr char kCkptMagic[8] = {'S', 'B', 'R', 'B', '2', '0', '0', '\0'};
+struct CkptBlob { char name[32]; uint64_t len, off; };
+static_assert(sizeof(sbr_hyper_values) == 88, "checkpoint layout documents an 88-byte sbr_hyper_values");
+static_assert(sizeof(CkptBlob) == 48, "checkpoint blob directory entry is 48 bytes");
+
+std::vector<std::string> ckpt_blob_names(const sbr_hyperparameters& h) {
+    std::vector<std::string> base = {"item_embeddings", "item_biases"};
+    if (h.model == MODEL_LSTM) { base.push_back("lstm_weights"); base.push_back("lstm_biases"); } else base.push_back("alpha");
+    std::vector<std::string> out;
+    for (const std::string& b : base) {
+        out.push_back(b); out.push_back(b + ".s1");
+        if (h.optimizer == SBR_OPTIMIZER_ADAM) out.push_back(b + ".s2");
+    }
+    return out;
+}
+struct FileCloser { FILE* f; ~FileCloser() { if (f) fclose(f); } };
+}  // namespace
+
+sbr_status sbr_model_save(const sbr_model* m, const char* path) {
+    if (!m || !path) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    sbr_status s = require_device();
+    if (s) return s;
+    const std::vector<std::string> names = ckpt_blob_names(m->h);
+    std::vector<CkptBlob> dir(names.size());
+    const uint64_t header = (128 + 8 + names.size() * sizeof(CkptBlob) + 63) / 64 * 64;
+    uint64_t off = header;
+    for (size_t i = 0; i < names.size(); ++i) {
+        std::memset(&dir[i], 0, sizeof(CkptBlob));
+        std::snprintf(dir[i].name, sizeof(dir[i].name), "%s", names[i].c_str());
+        size_t len = 0;
+        if ((s = sbr_model_parameter_len(m, names[i].c_str(), &len))) return s;
+        dir[i].len = len; dir[i].off = off; off += (uint64_t)len * 4;
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(SBR_ERR_INVALID_ARGUMENT, std::string("cannot open for writing: ") + path);
+    FileCloser fc{f};
+    std::vector<uint8_t> head(header, 0);
+    std::memcpy(head.data(), kCkptMagic, 8);
+    const uint32_t version = 1, hb = (uint32_t)header, nb = (uint32_t)names.size();
+    std::memcpy(head.data() + 8, &version, 4); std::memcpy(head.data() + 12, &hb, 4);
+    sbr_hyper_values hv; fill_hyper_values(m->h, &hv);
+    std::memcpy(head.data() + 16, &hv, sizeof(hv));
+    const uint32_t rs[4] = {m->rng.x, m->rng.y, m->rng.z, m->rng.w};
+    std::memcpy(head.data() + 104, rs, 16);
+    std::memcpy(head.data() + 120, &m->num_updates, 8);
+    std::memcpy(head.data() + 128, &nb, 4);
+    std::memcpy(head.data() + 136, dir.data(), dir.size() * sizeof(CkptBlob));
+    if (fwrite(head.data(), 1, head.size(), f) != head.size()) return fail(SBR_ERR_INVALID_ARGUMENT, "short write (header)");
+    std::vector<float> buf;
+    for (size_t i = 0; i < names.size(); ++i) {
+        buf.resize(dir[i].len);
+        if ((s = sbr_model_get_parameter(m, names[i].c_str(), buf.data(), buf.size()))) return s;
+        if (fwrite(buf.data(), 4, buf.size(), f) != buf.size()) return fail(SBR_ERR_INVALID_ARGUMENT, "short write (blob)");
+    }
+    return SBR_OK;
+}
+
+static sbr_status ckpt_read(const char* path, sbr_hyper_values* hv, uint32_t rs[4], uint64_t* num_updates, std::vector<CkptBlob>* dir, FILE** fout) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(SBR_ERR_INVALID_ARGUMENT, std::string("cannot open: ") + path);
+    uint8_t fixed[136];
+    uint32_t version = 0, hb = 0, nb = 0;
+    bool ok = fread(fixed, 1, sizeof(fixed), f) == sizeof(fixed) && std::memcmp(fixed, kCkptMagic, 8) == 0;
+    if (ok) { std::memcpy(&version, fixed + 8, 4); std::memcpy(&hb, fixed + 12, 4); std::memcpy(&nb, fixed + 128, 4); ok = version == 1 && nb <= 16 && hb >= 136 + nb * sizeof(CkptBlob); }
+    if (ok) { dir->resize(nb); ok = fread(dir->data(), sizeof(CkptBlob), nb, f) == nb; }
+    if (!ok) { fclose(f); return fail(SBR_ERR_INVALID_ARGUMENT, "not a version-1 sbr_b200 checkpoint"); }
+    std::memcpy(hv, fixed + 16, sizeof(*hv)); std::memcpy(rs, fixed + 104, 16); std::memcpy(num_updates, fixed + 120, 8);
+    for (CkptBlob& b : *dir) b.name[31] = 0;
+    *fout = f;
+    return SBR_OK;
+}
+
+static sbr_status ckpt_apply(sbr_model* m, const sbr_hyper_values& hv, const uint32_t rs[4], uint64_t num_updates, const std::vector<CkptBlob>& dir, FILE* f) {
+    if (hv.model != m->h.model || hv.num_items != m->h.num_items || hv.embedding_dim != m->h.embedding_dim || hv.optimizer != m->h.optimizer)
+        return fail(SBR_ERR_INVALID_ARGUMENT, "checkpoint does not match the model (model kind / num_items / embedding_dim / optimizer)");
+    std::vector<float> buf;
+    for (const CkptBlob& b : dir) {
+        size_t len = 0;
+        sbr_status s = sbr_model_parameter_len(m, b.name, &len);
+        if (s) return s;
+        if (len != b.len) return fail(SBR_ERR_INVALID_ARGUMENT, std::string("checkpoint blob has the wrong length: ") + b.name);
+        buf.resize(len);
+        if (fseek(f, (long)b.off, SEEK_SET) != 0 || fread(buf.data(), 4, len, f) != len) return fail(SBR_ERR_INVALID_ARGUMENT, std::string("truncated checkpoint blob: ") + b.name);
+        if ((s = sbr_model_set_parameter(m, b.name, buf.data(), len))) return s;
+    }
+    if ((rs[0] | rs[1] | rs[2] | rs[3]) == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "checkpoint holds an all-zero rng state");
+    m->rng.x = rs[0]; m->rng.y = rs[1]; m->rng.z = rs[2]; m->rng.w = rs[3];
+    m->num_updates = num_updates;
+    return SBR_OK;
+}
+
+sbr_status sbr_model_restore(sbr_model* m, const char* path) {
+    if (!m || !path) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    sbr_status s = require_device();
+    if (s) return s;
+    sbr_hyper_values hv; uint32_t rs[4]; uint64_t nu = 0; std::vector<CkptBlob> dir; FILE* f = nullptr;
+    if ((s = ckpt_read(path, &hv, rs, &nu, &dir, &f))) return s;
+    FileCloser fc{f};
+    return ckpt_apply(m, hv, rs, nu, dir, f);
+}
+
+sbr_status sbr_model_load(const char* path, sbr_model** out) {
+    if (!path || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    sbr_status s = require_device();
+    if (s) return s;
+    sbr_hyper_values hv; uint32_t rs[4]; uint64_t nu = 0; std::vector<CkptBlob> dir; FILE* f = nullptr;
+    if ((s = ckpt_read(path, &hv, rs, &nu, &dir, &f))) return s;
+    FileCloser fc{f};
+    if (hv.model != MODEL_LSTM && hv.model != MODEL_EWMA) return fail(SBR_ERR_INVALID_ARGUMENT, "checkpoint: unknown model kind");
+    sbr_hyperparameters* h = hyper_new(hv.model, hv.num_items, hv.max_sequence_length);
+    if (!h) return fail(SBR_ERR_INVALID_ARGUMENT, "out of memory");
+    h->embedding_dim = hv.embedding_dim; h->learning_rate = hv.learning_rate; h->l2_penalty = hv.l2_penalty;
+    h->lstm_variant = hv.lstm_variant; h->loss = hv.loss; h->optimizer = hv.optimizer; h->parallelism = hv.parallelism;
+    h->num_threads = hv.num_threads; h->num_epochs = hv.num_epochs; h->exact = hv.exact_arithmetic;
+    std::memcpy(h->seed, hv.seed, 16);
+    sbr_model* m = nullptr;
+    if ((s = sbr_hyper_build(h, &m))) return s;
+    if ((s = ckpt_apply(m, hv, rs, nu, dir, f))) { const std::string keep = g_err; sbr_model_free(m); g_err = keep; return s; }
+    *out = m;
     return SBR_OK;
 }
 
@@ -889,6 +1077,9 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     if (P == 0) {
         const size_t autoP = (size_t)train_auto_partitions(m->dev, device_info().sms);
         P = std::min(autoP, std::max<size_t>(1, nsub / 16));
+        // the LSTM tile kernels take whole tiles of 128 partitions (2 tiles per CTA): round down so that real data
+        // (nsub / 16 is almost never a multiple of 128) still runs on them
+        if (m->dev.model == MODEL_LSTM && m->dev.D == 32) { if (P >= 256) P -= P % 256; else if (P >= 128) P = 128; }
     }
     if (P > nsub) return fail(SBR_ERR_INVALID_ARGUMENT, "num_threads exceeds the number of sub-sequences (the reference panics in chunks_mut(0))");
     const size_t n = nsub / P;  // :91, remainder dropped by the zip at :94-96
@@ -967,7 +1158,6 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
     cudaStream_t st = m->stream;
     const size_t P = pl->P;
     pl->dev.epochs = (int)m->h.num_epochs;
-    { const char* f = getenv("SBR_DBG_FLAGS"); pl->dev.dbg_flags = f ? atoi(f) : 0; }
     pl->dev.adam_t0 = m->num_updates;
     CU(cudaMemsetAsync(pl->dev.loss_acc, 0, P * sizeof(float), st));
     CU(cudaMemsetAsync(pl->dev.examples, 0, P * sizeof(unsigned long long), st));
@@ -984,7 +1174,10 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
             return fail(SBR_ERR_NCCL, "synchronous multi-GPU fit needs sbr_dist_init(rank, world, id) matching sbr_hyper_shard");
         if (!pl->sync) pl->sync = sync_buffers_new();
         std::string err;
-        const int rc = run_sync_ewma(m->dev, pl->dev, *pl->sync, g_comm, m->h.shard_rank, world, m->num_updates, st, &launches, &sync_rounds, &err);
+        // every rank steps its OWN replica of the dense parameters (after sbr_model_ipc_attach dev.dense of rank != 0 points
+        // at rank 0's buffer, which all ranks would otherwise step once each per round)
+        ModelDev md = m->dev; md.dense = m->own_dense;
+        const int rc = run_sync_ewma(md, pl->dev, *pl->sync, g_comm, m->h.shard_rank, world, m->num_updates, st, &launches, &sync_rounds, &err);
         if (rc) return fail(rc == 2 ? SBR_ERR_NCCL : rc == 3 ? SBR_ERR_INVALID_ARGUMENT : SBR_ERR_CUDA, err);
     } else if (pl->dev.epochs > 0) {
         if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before an asynchronous fit");
@@ -1124,7 +1317,7 @@ sbr_status sbr_model_mrr_score(const sbr_model* m, const sbr_compressed* test, f
         CU(cudaMalloc(&d_rr, U * sizeof(float)));
         cudaError_t e = cudaMalloc(&d_flag, sizeof(int));
         if (e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, sizeof(int), st);
-        if (e == cudaSuccess) e = launch_mrr(m->dev, test->d_user_ptr, test->d_item_ids, U, d_rr, d_flag, st);
+        if (e == cudaSuccess) e = launch_mrr(m->dev, (uint32_t)test->num_items, test->d_user_ptr, test->d_item_ids, U, d_rr, d_flag, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(rr.data(), d_rr, U * sizeof(float), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -28,6 +28,7 @@ struct ModelDev {
     float* dense;    // [3][ndense]  w | s1 | s2  (LSTM: W[2D][4][D] then bias[4][D]; EWMA: alpha[D])
     size_t ndense;
     float lr, l2;
+    int exact;       // sbr_hyper_exact_arithmetic: never use the tf32 / bf16 tile kernel
 };
 
 // Device-resident schedule of one fit(): sequence_model.rs:74-98 materialised in HBM
@@ -47,7 +48,6 @@ struct PlanDev {
     float* scratch;             // warp-private activations for backward
     size_t scratch_stride;      // floats per warp
     int epochs;
-    int dbg_flags;              // debugging switches (0 in production)
     unsigned long long adam_t0; // model num_updates before this run
 };
 
@@ -64,9 +64,7 @@ size_t train_scratch_floats_per_warp(const ModelDev& m);
 int train_auto_partitions(const ModelDev& m, int num_sms);
 bool train_supported(const ModelDev& m, const char** why);
 int lstm_kernel_choice(const ModelDev& m, uint32_t P);
-cudaError_t launch_lstm_tc(const ModelDev& m, const PlanDev& p, int nt, cudaStream_t st);
-cudaError_t launch_lstm_tc2(const ModelDev& m, const PlanDev& p, int nt, bool fast_math, cudaStream_t st);
-cudaError_t launch_lstm_tc3(const ModelDev& m, const PlanDev& p, int nt, int ds, cudaStream_t st);
+cudaError_t launch_lstm_tc3(const ModelDev& m, const PlanDev& p, int nt, cudaStream_t st);
 
 // round-synchronous engine (sync_engine.cu)
 struct SyncBuffers;
@@ -90,7 +88,8 @@ cudaError_t launch_user_representations(const ModelDev& m, const uint64_t* ptr_d
 cudaError_t launch_predict(const ModelDev& m, const float* user_dev, const uint32_t* ids_dev, size_t k, float* out_dev,
                            int* nonfinite_dev, cudaStream_t st);
 // reciprocal rank per user with >= 2 interactions (0 for the others); evaluation.rs:12-48
-cudaError_t launch_mrr(const ModelDev& m, const uint64_t* ptr_dev, const uint32_t* ids_dev, size_t num_users, float* rr_dev,
+// items 0..num_items (the TEST set's num_items, evaluation.rs:16) are scored and ranked
+cudaError_t launch_mrr(const ModelDev& m, uint32_t num_items, const uint64_t* ptr_dev, const uint32_t* ids_dev, size_t num_users, float* rr_dev,
                        int* nonfinite_dev, cudaStream_t st);
 cudaError_t launch_init_embeddings(const ModelDev& m, uint64_t seed, cudaStream_t st);
 // strided copy between packed host-order blobs and the record layouts

@@ -135,13 +135,13 @@ __global__ void __launch_bounds__(256) predict_kernel(ModelDev m, const float* _
 
 // mrr_score: one CTA per user (grid-strided).  pred is a [gridDim][N] scratch.
 template <int D>
-__global__ void __launch_bounds__(256) mrr_kernel(ModelDev m, const uint64_t* __restrict__ ptr,
+__global__ void __launch_bounds__(256) mrr_kernel(ModelDev m, uint32_t num_items, const uint64_t* __restrict__ ptr,
                                                   const uint32_t* __restrict__ ids, size_t num_users, float* pred_all,
                                                   float* rr, int* nonfinite) {
     __shared__ float user[D];
     __shared__ float zb[2 * D];
     __shared__ unsigned int cnt;
-    float* pred = pred_all + (size_t)blockIdx.x * m.N;
+    float* pred = pred_all + (size_t)blockIdx.x * num_items;   // evaluation.rs:16: 0..test.num_items()
     for (size_t u = blockIdx.x; u < num_users; u += gridDim.x) {
         const uint64_t b = ptr[u], e = ptr[u + 1];
         const uint64_t len = e - b;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) mrr_kernel(ModelDev m, const uint64_t* __
         if (threadIdx.x < 32) represent<D>(m, ids + hb, (int)hn, threadIdx.x, user, zb);  // :27
         if (threadIdx.x == 0) cnt = 0;
         __syncthreads();
-        for (uint32_t j = threadIdx.x; j < m.N; j += blockDim.x) {               // :16,28 all items
+        for (uint32_t j = threadIdx.x; j < num_items; j += blockDim.x) {          // :16,28 all items of the TEST set
             const float v = score_item<D>(m, user, j);
             if (!isfinite(v)) atomicOr(nonfinite, 1);
             pred[j] = v;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) mrr_kernel(ModelDev m, const uint64_t* __
         __syncthreads();
         const float ts = pred[test_item];                                        // :34
         unsigned int local = 0;
-        for (uint32_t j = threadIdx.x; j < m.N; j += blockDim.x) local += pred[j] >= ts ? 1u : 0u;  // :37-41
+        for (uint32_t j = threadIdx.x; j < num_items; j += blockDim.x) local += pred[j] >= ts ? 1u : 0u;  // :37-41
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) local += __shfl_xor_sync(kFull, local, o);
         if ((threadIdx.x & 31) == 0) atomicAdd(&cnt, local);
@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(ModelDev m, int slot, co
 }
 __global__ void __launch_bounds__(256) pack_bias_kernel(ModelDev m, int slot, const float* __restrict__ packed, float* out, int dir) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m.N; i += (size_t)gridDim.x * blockDim.x) {
+        if (dir == 0 && m.own_shard >= 0 && (int)(i & m.gmask) != m.own_shard) continue;   // peers' shards are theirs to write
         float* cell = reinterpret_cast<float*>(bias_rec(m, i)) + slot;
         if (dir == 0) *cell = packed[i]; else out[i] = *cell;
     }
@@ -250,14 +251,14 @@ cudaError_t launch_predict(const ModelDev& m, const float* user, const uint32_t*
     return cudaGetLastError();
 }
 
-cudaError_t launch_mrr(const ModelDev& m, const uint64_t* ptr, const uint32_t* ids, size_t num_users, float* rr,
+cudaError_t launch_mrr(const ModelDev& m, uint32_t num_items, const uint64_t* ptr, const uint32_t* ids, size_t num_users, float* rr,
                        int* nonfinite, cudaStream_t st) {
     if (num_users == 0) return cudaSuccess;
     int grid = (int)(num_users < 148 * 2 ? num_users : 148 * 2);
     float* pred = nullptr;
-    cudaError_t e = cudaMallocAsync(&pred, sizeof(float) * (size_t)grid * m.N, st);
+    cudaError_t e = cudaMallocAsync(&pred, sizeof(float) * (size_t)grid * num_items, st);
     if (e != cudaSuccess) return e;
-    SBR_DISPATCH_D(m.D, mrr_kernel<kD><<<grid, 256, 0, st>>>(m, ptr, ids, num_users, pred, rr, nonfinite));
+    SBR_DISPATCH_D(m.D, mrr_kernel<kD><<<grid, 256, 0, st>>>(m, num_items, ptr, ids, num_users, pred, rr, nonfinite));
     e = cudaGetLastError();
     cudaFreeAsync(pred, st);
     return e;

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
     };
     // The sparse visits of one backward timestep, this warp's chunks of the 32 rows (flags as in kernels_lstm_tc2.cu):
     //   bit 0: E[neg] += step(+g h)      bit 1: visit E[out]: [bit 2: step(dx_{t+1})] [bit 3: step(+g h)] [bit 4: step(-g h)]
-    const bool noatom = (pl.dbg_flags & 8) != 0 || m.hbm_resident != 0;   // hot rows only exist on L2-resident tables
+    const bool noatom = m.hbm_resident != 0;   // hot rows only exist on L2-resident tables
     // A pass covers GPP row groups (NGI / GPP passes per timestep).  It is split in two so that the round trip of the
     // first pass -- {ld w, atom G} or {ld w, ld G} -- flies while the tile meets at its barrier and the MMAs are issued.
     constexpr int GPP = NGI >= 2 ? 2 : 1;   // row groups per pass: 4 row visits (w, s each) in flight
@@ -837,12 +837,8 @@ cudaError_t launch_one(const ModelDev& m, const PlanDev& p, cudaStream_t st) {
 
 }  // namespace
 
-cudaError_t launch_lstm_tc3(const ModelDev& m, const PlanDev& p, int nt, int ds, cudaStream_t st) {
+cudaError_t launch_lstm_tc3(const ModelDev& m, const PlanDev& p, int nt, cudaStream_t st) {
     const bool flat = m.gmask == 0;
-    if (ds == 4) {   // experiment only: 64 registers per thread spill
-        if (nt == 2) return flat ? launch_one<2, 4, true>(m, p, st) : launch_one<2, 4, false>(m, p, st);
-        return flat ? launch_one<1, 4, true>(m, p, st) : launch_one<1, 4, false>(m, p, st);
-    }
     if (nt == 2) return flat ? launch_one<2, 2, true>(m, p, st) : launch_one<2, 2, false>(m, p, st);
     return flat ? launch_one<1, 2, true>(m, p, st) : launch_one<1, 2, false>(m, p, st);
 }

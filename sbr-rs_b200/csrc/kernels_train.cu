@@ -6,8 +6,6 @@
 // lock-free in HBM/L2 exactly like Arc<HogwildParameter> (lstm.rs:175-181,259-260).  One launch runs all epochs.
 #include <cuda_runtime.h>
 
-#include <cstdlib>
-#include <cstring>
 
 #include "engine.h"
 
@@ -115,7 +113,7 @@ __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl)
     OptCfg o; o.lr = m.lr; o.l2 = m.l2; o.adam = m.opt == 1; o.c1 = 1.0f; o.c2 = 1.0f;
     // Hogwild with more than one partition: Adagrad visits go through L2 atomics (common.cuh); one partition keeps
     // the plain load / store visit, which is the reference's single-thread arithmetic to the last bit
-    const bool atomics = !o.adam && pl.P > 1 && !m.hbm_resident && !(pl.dbg_flags & 8);   // (HBM-resident tables: no hot rows, plain visits are 8 % faster)
+    const bool atomics = !o.adam && pl.P > 1 && !m.hbm_resident;   // (HBM-resident tables: no hot rows, plain visits are 8 % faster)
 
     for (int ep = 0; ep < pl.epochs; ++ep) {
         if (lane == 0) shuffle_partition(ord, pl.n, rng);
@@ -769,12 +767,10 @@ int train_auto_partitions(const ModelDev& m, int num_sms) {
     return num_sms * per_sm;
 }
 
-// which LSTM kernel a plan runs on: 0 = FFMA (exact fp32, warp per partition), 1/2 = tensor-core tiles per CTA
+// which LSTM kernel a plan runs on: 0 = FFMA (exact fp32, warp per partition), 1 / 2 = tensor-core tiles per CTA.
+// The tile kernel takes whole tiles of 128 partitions; sbr_hyper_exact_arithmetic(h, 1) keeps the exact path.
 int lstm_kernel_choice(const ModelDev& m, uint32_t P) {
-    const char* force = getenv("SBR_LSTM_KERNEL");
-    if (force && !strcmp(force, "ffma")) return 0;
-    if (m.model != MODEL_LSTM || m.D != 32 || P < 128 || P % 128 != 0) return 0;
-    if (force && !strcmp(force, "tc1")) return 1;
+    if (m.exact || m.model != MODEL_LSTM || m.D != 32 || P < 128 || P % 128 != 0) return 0;
     return P % 256 == 0 ? 2 : 1;
 }
 
@@ -792,19 +788,7 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
             default: *err = cudaErrorInvalidValue; return 0;
         }
     } else if (int nt = lstm_kernel_choice(m, p.P)) {
-        // SBR_LSTM_TC selects the tile-kernel generation (default "3"): "1" = kernels_lstm_tc.cu (thread per sequence),
-        // "2" = kernels_lstm_tc2.cu (+ cp.async prefetch pipeline, merged visits, L2-atomic Adagrad), "2f" = the same
-        // with MUFU.TANH gates, "3" / "34" = kernels_lstm_tc3.cu with 2 / 4 threads per sequence
-        const char* gen = getenv("SBR_LSTM_TC");
-        // Row-sharded tables (peer rows over NVLink) default to generation 1: it fetches WARP candidates only when a
-        // try needs them, and small remote requests are what NVLink is worst at -- measured on 2 GPUs sharing the
-        // ML-100K-shaped model: generation 1 23.3 M steps/s, generations 2 / 3 (all five candidates prefetched) 13 M.
-        if (!gen) gen = m.gmask != 0 ? "1" : "3";
-        if (!strcmp(gen, "1")) *err = launch_lstm_tc(m, p, nt, st);
-        else if (!strcmp(gen, "2")) *err = launch_lstm_tc2(m, p, nt, false, st);
-        else if (!strcmp(gen, "2f")) *err = launch_lstm_tc2(m, p, nt, true, st);
-        else if (!strcmp(gen, "34")) *err = launch_lstm_tc3(m, p, nt, 4, st);
-        else *err = launch_lstm_tc3(m, p, nt, 2, st);
+        *err = launch_lstm_tc3(m, p, nt, st);
         return 1;
     } else {
         dim3 block(kLstmWPC * 32), grid((p.P + kLstmWPC - 1) / kLstmWPC);

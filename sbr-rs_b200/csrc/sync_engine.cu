@@ -295,22 +295,31 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
     if (world > 1) { NC = nccl_api(err); if (!NC) return 2; }
     const int G = world, D = m.D, Tm1 = m.T - 1;
     const size_t nslots = (size_t)pl.P * Tm1 * 3;
-    const size_t cap_own = world == 1 ? nslots : nslots * 3 / 2 + 4096;  // rows other ranks may request from this shard per round
+    // Rows other ranks may request from this shard per round.  The usual load is ~nslots; a skewed id distribution (popular
+    // ids in one residue class mod world) can send up to world * nslots rows to one owner, so the owner-side buffers GROW
+    // when a round needs more (the stream is idle at that point: the counts were just read back).
+    size_t cap_own = 0;
+    auto ensure_own = [&](size_t need) -> int {
+        if (need <= cap_own) return 0;
+        cap_own = need;
+        SCU(B.keys_in.ensure(cap_own * 8)); SCU(B.keys_out.ensure(cap_own * 8)); SCU(B.vals_in.ensure(cap_own * 4)); SCU(B.vals_out.ensure(cap_own * 4));
+        size_t cub_bytes = 0;
+        SCU(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<unsigned long long*>(nullptr), static_cast<unsigned long long*>(nullptr),
+                                            static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), (int)cap_own, 0, 64, st));
+        SCU(B.cub_tmp.ensure(cub_bytes));
+        if (world > 1) {
+            SCU(B.recv_row.ensure(cap_own * 4)); SCU(B.recv_ord.ensure(cap_own * 4)); SCU(B.rows_own.ensure(cap_own * D * 4)); SCU(B.bias_own.ensure(cap_own * 4));
+            SCU(B.grads_own.ensure(cap_own * D * 4)); SCU(B.bgrads_own.ensure(cap_own * 4));
+        }
+        return 0;
+    };
     SCU(B.req_id.ensure(nslots * 4)); SCU(B.send_row.ensure(nslots * 4)); SCU(B.pos_of_slot.ensure(nslots * 4));
     SCU(B.req_ord.ensure(nslots * 4)); SCU(B.send_ord.ensure(nslots * 4));
-    SCU(B.keys_in.ensure(cap_own * 8)); SCU(B.keys_out.ensure(cap_own * 8)); SCU(B.vals_in.ensure(cap_own * 4)); SCU(B.vals_out.ensure(cap_own * 4));
-    size_t cub_bytes = 0;
-    SCU(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<unsigned long long*>(nullptr), static_cast<unsigned long long*>(nullptr),
-                                        static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), (int)cap_own, 0, 64, st));
-    SCU(B.cub_tmp.ensure(cub_bytes));
+    if (int rc = ensure_own(world == 1 ? nslots : nslots * 3 / 2 + 4096)) return rc;
     SCU(B.counts.ensure(64)); SCU(B.allcounts.ensure(8 * 8 * 4));
     SCU(B.rows_req.ensure(nslots * D * 4)); SCU(B.bias_req.ensure(nslots * 4));
     SCU(B.grads_req.ensure(nslots * D * 4)); SCU(B.bgrads_req.ensure(nslots * 4));
     SCU(B.dalpha.ensure(m.ndense * 4));
-    if (world > 1) {
-        SCU(B.recv_row.ensure(cap_own * 4)); SCU(B.recv_ord.ensure(cap_own * 4)); SCU(B.rows_own.ensure(cap_own * D * 4)); SCU(B.bias_own.ensure(cap_own * 4));
-        SCU(B.grads_own.ensure(cap_own * D * 4)); SCU(B.bgrads_own.ensure(cap_own * 4));
-    }
     if (!B.h_counts) SCU(cudaHostAlloc(&B.h_counts, (8 * 8 + 8) * sizeof(unsigned int), cudaHostAllocDefault));
     SCU(cudaMemsetAsync(B.dalpha.p, 0, m.ndense * 4, st));
     unsigned int* counts = static_cast<unsigned int*>(B.counts.p);       // [0..8) counts, [8..16) cursors
@@ -327,11 +336,12 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
                         size_t elem) -> ncclResult_t {
         ncclResult_t r = NC->GroupStart();
         if (r != ncclSuccess) return r;
-        for (int g = 0; g < G; ++g) {
-            if (scnt[g]) { r = NC->Send(static_cast<const char*>(sendbuf) + soff[g] * elem, scnt[g] * elem, ncclChar, g, comm, st); if (r != ncclSuccess) return r; }
-            if (rcnt[g]) { r = NC->Recv(static_cast<char*>(recvbuf) + roff[g] * elem, rcnt[g] * elem, ncclChar, g, comm, st); if (r != ncclSuccess) return r; }
+        for (int g = 0; g < G && r == ncclSuccess; ++g) {
+            if (scnt[g]) r = NC->Send(static_cast<const char*>(sendbuf) + soff[g] * elem, scnt[g] * elem, ncclChar, g, comm, st);
+            if (r == ncclSuccess && rcnt[g]) r = NC->Recv(static_cast<char*>(recvbuf) + roff[g] * elem, rcnt[g] * elem, ncclChar, g, comm, st);
         }
-        return NC->GroupEnd();
+        const ncclResult_t re = NC->GroupEnd();   // the group is always closed, also after a failed Send / Recv
+        return r != ncclSuccess ? r : re;
     };
 
     // every rank must run the same number of rounds (collectives inside): the ranks agree on the smallest partition length
@@ -367,7 +377,7 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
                     rcnt[g] = B.h_counts[g * 8 + rank]; roff[g] = ro; ro += rcnt[g];
                 }
                 nown = ro;
-                if (nown > cap_own) { *err = "sync exchange: more rows requested from this shard than the receive capacity"; return 3; }
+                if (int rc = ensure_own(nown)) return rc;
                 // 2. ids to owners
                 SNC(exchange(send_row, scnt, soff, B.recv_row.p, rcnt, roff, 4));
                 SNC(exchange(send_ord, scnt, soff, B.recv_ord.p, rcnt, roff, 4));

@@ -1,4 +1,5 @@
-// debug_tc.cu -- unit-test entry for the tcgen05 tile primitives (not part of the public ABI; symbol prefix sbrdbg_).
+// tc_primitives_hook.cu -- unit-test entry for the tcgen05 tile primitives of sbr-rs_b200/csrc/tc_tile.cuh.  Test
+// infrastructure: built into its own tests/csrc/libtc_primitives_hook.so, never linked into libsbr_b200.so.
 // Runs the three GEMM shapes of the tensor-core LSTM kernel on caller-provided row-major matrices:
 //   mode 1: D[128x128] = Z[128x80](:, :64) . W[64x128]     tf32  (gates:  A K-major,  B K-major)
 //   mode 2: D[128x64]  = Dl[128x128] . W[64x128]^T         bf16  (dz:     A K-major,  B K-major)

@@ -100,6 +100,52 @@ def test_hyperparameter_builder_chains(pkg):
     assert isinstance(h, pkg.lstm.Hyperparameters)
 
 
+def test_hyper_values_and_defaults(pkg):
+    """Defaults of Hyperparameters::new (lstm.rs:56-71 / ewma.rs:61-76) read back through sbr_hyper_get_values."""
+    v = pkg.lstm.Hyperparameters(100, 32).values()
+    assert (v["model"], v["num_items"], v["max_sequence_length"], v["embedding_dim"]) == (0, 100, 32, 16)
+    assert abs(v["learning_rate"] - 0.01) < 1e-9 and v["l2_penalty"] == 0.0
+    assert (v["lstm_variant"], v["loss"], v["optimizer"], v["parallelism"]) == (
+        pkg.LSTMVariant.Coupled, pkg.Loss.BPR, pkg.Optimizer.Adam, pkg.Parallelism.Synchronous)
+    assert v["num_epochs"] == 10 and v["exact_arithmetic"] == 0
+    h = pkg.ewma.Hyperparameters(7, 5).from_seed(bytes(range(16))).exact_arithmetic().num_threads(3)
+    v = h.values()
+    assert (v["model"], v["seed"], v["exact_arithmetic"], v["num_threads"]) == (1, bytes(range(16)), 1, 3)
+
+
+@pytest.mark.parametrize("kind", ["lstm", "ewma"])
+def test_hyperparameters_random(pkg, kind):
+    """Hyperparameters::random (lstm.rs:141-172 / ewma.rs:139-170): every field inside the reference's ranges, the
+    caller's rng advances, the same rng state gives the same draw, and over many draws every branch is taken."""
+    H = pkg.lstm.Hyperparameters if kind == "lstm" else pkg.ewma.Hyperparameters
+    st = (1, 2, 3, 4)
+    seen = {"loss": set(), "optimizer": set(), "parallelism": set(), "lstm_variant": set(), "T": set(), "D": set(), "epochs": set()}
+    first = None
+    for i in range(200):
+        h, st2 = H.random(1683, st)
+        v = h.values()
+        if first is None:
+            first = v
+            h_again, st_again = H.random(1683, st)
+            va = h_again.values()
+            assert st_again == st2 and {k: va[k] for k in va if k != "seed"} == {k: v[k] for k in v if k != "seed"}
+        assert st2 != st
+        st = st2
+        assert v["num_items"] == 1683
+        assert v["max_sequence_length"] in (16, 32, 64, 128) and v["embedding_dim"] in (16, 32, 64, 128)
+        assert 1e-3 <= v["learning_rate"] < 10 ** 0.5 + 1e-6 and 1e-7 <= v["l2_penalty"] < 1e-3 + 1e-9
+        assert v["loss"] in (pkg.Loss.BPR, pkg.Loss.Hinge) and v["optimizer"] in (0, 1) and v["parallelism"] in (0, 1)
+        assert 1 <= v["num_threads"] <= (os.cpu_count() or 1) and v["num_epochs"] in (8, 16, 32, 64)
+        for k, f in (("loss", "loss"), ("optimizer", "optimizer"), ("parallelism", "parallelism"), ("lstm_variant", "lstm_variant"),
+                     ("T", "max_sequence_length"), ("D", "embedding_dim"), ("epochs", "num_epochs")):
+            seen[k].add(v[f])
+    assert seen["loss"] == {0, 1} and seen["optimizer"] == {0, 1} and seen["parallelism"] == {0, 1}
+    assert seen["T"] == {16, 32, 64, 128} and seen["D"] == {16, 32, 64, 128} and seen["epochs"] == {8, 16, 32, 64}
+    assert seen["lstm_variant"] == ({0, 1} if kind == "lstm" else {pkg.LSTMVariant.Coupled})
+    with pytest.raises(pkg.SbrError):
+        H.random(10, (0, 0, 0, 0))
+
+
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="this check is for GPU-less boxes")
 def test_compute_fails_loudly_without_gpu(pkg):
     assert pkg.device_count() == 0
