@@ -30,12 +30,33 @@ A_TRAIN_BYTES_PER_TIMESTEP = 60 * DIM + 52  # gather 12D+20 + Adagrad
 METRIC = "user-seq steps/sec"
 
 
-def make_stream(num_seqs, seed):
-    """2^k synthetic users x exactly 32 items, uniform over [1, N) (SURVEY 8d 'C2-stream', headline variant)."""
+def make_stream(num_seqs, seed, zipf=False):
+    """2^k synthetic users x exactly 32 items (SURVEY 8d 'C2-stream'): uniform over [1, N) -- the headline variant -- or
+    Zipf(1.0) over the same ids (p(rank k) ~ 1/k: the hot-row case, item 1 alone draws 13 % of all interactions)."""
     rng = np.random.default_rng(seed)
     ptr = np.arange(num_seqs + 1, dtype=np.uint64) * np.uint64(SEQ_LEN)
-    ids = rng.integers(1, NUM_ITEMS, size=num_seqs * SEQ_LEN, dtype=np.uint64)
+    if zipf:
+        cdf = np.cumsum(1.0 / np.arange(1, NUM_ITEMS, dtype=np.float64))
+        ids = (1 + np.searchsorted(cdf / cdf[-1], rng.random(num_seqs * SEQ_LEN))).astype(np.uint64)
+        ids = np.minimum(ids, NUM_ITEMS - 1)
+    else:
+        ids = rng.integers(1, NUM_ITEMS, size=num_seqs * SEQ_LEN, dtype=np.uint64)
     return ptr, ids
+
+
+def gather_leg(pkg):
+    """BASELINE.json metric, second leg: "embed-gather HBM GB/s vs roofline".  Stand-alone gather_rows_kernel on an
+    HBM-resident table (8 M items x dim 128 with its Adagrad state: 8 GB, far beyond L2), 4 M uniform random row ids per
+    launch, timed by the library with CUDA events on its stream (sbr_model_gather_rows_timed, mean of 5 launches after a
+    warm-up).  Algorithmic bytes per row: 4 D read + 4 D written + 4 (u32 id)."""
+    N, D, rows = 8 << 20, 128, 4 << 20
+    m = (pkg.ewma.Hyperparameters(N, 8).embedding_dim(D).optimizer(pkg.Optimizer.Adagrad).from_seed(bytes(range(16)))).build()
+    ids = np.random.default_rng(7).integers(0, N, size=rows, dtype=np.uint64)
+    ms = m.gather_rows_timed(ids, iters=5)
+    nbytes = rows * (8 * D + 4)
+    del m
+    return {"GB/s": nbytes / (ms * 1e-3) / 1e9, "ms_per_launch": ms, "rows_per_launch": rows, "num_items": N, "dim": D,
+            "table_bytes": N * D * 4 * 2, "algorithmic_bytes_per_row": 8 * D + 4, "kernel": "gather_rows_kernel"}
 
 
 def peaks():
@@ -201,9 +222,11 @@ def main():
     # N > 1: ONE model shared by all ranks -- the item table is row-sharded (id % N) and every rank's kernel reads /
     # updates remote rows in the owner's HBM over NVLink (CUDA-IPC peer mappings); no collective on the data path.
     seed = bytes(range(16))  # same init on every rank
-    hyper = (pkg.lstm.Hyperparameters(NUM_ITEMS, SEQ_LEN).embedding_dim(DIM).learning_rate(LR).l2_penalty(L2)
-             .lstm_variant(pkg.LSTMVariant.Normal).loss(pkg.Loss.WARP).optimizer(pkg.Optimizer.Adagrad)
-             .parallelism(pkg.Parallelism.Asynchronous).num_epochs(1).num_threads(args.threads).from_seed(seed))
+    def hyper_factory():
+        return (pkg.lstm.Hyperparameters(NUM_ITEMS, SEQ_LEN).embedding_dim(DIM).learning_rate(LR).l2_penalty(L2)
+                .lstm_variant(pkg.LSTMVariant.Normal).loss(pkg.Loss.WARP).optimizer(pkg.Optimizer.Adagrad)
+                .parallelism(pkg.Parallelism.Asynchronous).num_epochs(1).num_threads(args.threads).from_seed(seed))
+    hyper = hyper_factory()
     multi = os.environ.get("SBR_BENCH_MULTI", "replicas") if world > 1 else "single"
     sync = None
     if multi == "shared":
@@ -241,9 +264,27 @@ def main():
     clocks = sampler.stop()
     partitions = plan.stats()["partitions"]
     steps_done = plan.stats()["steps"]  # per run
+    kernel_name = plan.stats()["kernel"]
     value = world * steps_done * args.steps / wall
     kernel_ms_max = max_over_ranks(kernel_ms)
     del plan
+
+    # ---------------- Zipf(1.0) variant of the same stream (SURVEY 8d "report both"), device-resident, rank 0's number ----
+    zipf = None
+    if world == 1:
+        zptr, zids = make_stream(S, 2000 + rank, zipf=True)
+        zdata = pkg.CompressedInteractions.from_csr(zptr, zids, None, num_items=NUM_ITEMS).upload()
+        zmodel = hyper_factory().build()
+        zplan = zmodel.fit_plan(zdata)
+        for _ in range(args.warmup):
+            zplan.run()
+        zms, zts = 0.0, 0
+        for _ in range(args.steps):
+            zplan.run()
+            zms += zplan.stats()["train_kernel_ms"]; zts += zplan.stats()["timesteps"]
+        zipf = {"value": zplan.stats()["steps"] * args.steps / (zms * 1e-3), "unit": "steps/s", "timed": "CUDA events around the kernel",
+                "frac": A_TRAIN_BYTES_PER_TIMESTEP * zts / (zms * 1e-3) / 1e9 / peaks()[0], "item_distribution": "Zipf(1.0) over [1,N)"}
+        del zplan, zmodel, zdata, zids
 
     # ---------------- end-to-end arm through the C ABI from host buffers: `e2e` ----------------
     h2d = d2h = 0
@@ -270,12 +311,18 @@ def main():
     if rank == 0:
         peak, peak_kind = peaks()
         per_launch_bytes = A_TRAIN_BYTES_PER_TIMESTEP * (timesteps / max(launches, 1))
-        traffic = None  # DRAM bytes per launch from the committed ncu --set full capture (scaled to this launch size)
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                tj = json.load(f)
-            traffic = tj["dram_bytes_per_launch"] * (steps_done / tj["seqs_per_launch"])
+        # DRAM bytes per launch: NOT measured in this run -- taken from the committed `ncu --set full` capture of the same
+        # kernel on the same workload (dram__bytes_read.sum + dram__bytes_write.sum), scaled by sequences per launch
+        traffic, traffic_src = None, None
+        for tname in ("r2_traffic.json", "r1_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    tj = json.load(f)
+                traffic = tj["dram_bytes_per_launch"] * (steps_done / tj["seqs_per_launch"])
+                traffic_src = "profiles/%s (ncu --set full capture of %s, %d sequences per launch; scaled to this launch)" % (
+                    tname, tj.get("kernel", "the tile kernel"), tj["seqs_per_launch"])
+                break
         per_launch_ms = kernel_ms / max(launches, 1)
         achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
         out = {
@@ -295,10 +342,15 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_kind": peak_kind, "kernel": ("lstm_tc3_train_kernel<2,2> (tcgen05 tile kernel, 2 threads per sequence)" if multi != "shared" else
-                                    "lstm_tc_train_kernel<2> (tcgen05 tile kernel, generation 1: row-sharded table over NVLink)"),
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind, "kernel": kernel_name,
                          "algorithmic_bytes_per_timestep": A_TRAIN_BYTES_PER_TIMESTEP},
         }
+        if zipf:
+            out["zipf"] = zipf
+        if world == 1:
+            gl = gather_leg(pkg)
+            gl["peak"] = peak; gl["frac"] = gl["GB/s"] / peak
+            out["gather"] = gl
         if not args.no_cpu_baseline:
             n = args.cpu_seqs or 1024 * cores
             cv, csec = cpu_reference_run(n, 2, 1, cores)

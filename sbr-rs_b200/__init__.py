@@ -70,10 +70,13 @@ class FitStats(C.Structure):
         ("steps", C.c_uint64), ("timesteps", C.c_uint64), ("partitions", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
         ("train_kernel_ms", C.c_double), ("total_device_ms", C.c_double), ("host_prepare_ms", C.c_double),
+        ("kernel", C.c_char * 64),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["kernel"] = d["kernel"].decode()
+        return d
 
 
 class FittingError(Exception):

@@ -59,7 +59,7 @@ __device__ __forceinline__ float4* bias_rec(const ModelDev& m, uint32_t id) { re
 #endif
 
 // launchers (kernels_train.cu / kernels_infer.cu); all enqueue on `st` and return the launch count
-int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t st, cudaError_t* err);
+int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t st, cudaError_t* err, const char** kernel_name);
 size_t train_scratch_floats_per_warp(const ModelDev& m);
 int train_auto_partitions(const ModelDev& m, int num_sms);
 bool train_supported(const ModelDev& m, const char** why);

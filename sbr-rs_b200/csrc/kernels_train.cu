@@ -774,10 +774,14 @@ int lstm_kernel_choice(const ModelDev& m, uint32_t P) {
     return P % 256 == 0 ? 2 : 1;
 }
 
-int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t st, cudaError_t* err) {
+int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t st, cudaError_t* err, const char** kernel_name) {
     (void)num_sms;
     *err = cudaSuccess;
+    const char* dummy; const char*& kn = kernel_name ? *kernel_name : dummy;
+    kn = "";
     if (m.model == MODEL_EWMA) {
+        kn = m.D == 16 ? "ewma_train_kernel<16>" : m.D == 32 ? "ewma_train_kernel<32>" : m.D == 64 ? "ewma_train_kernel<64>"
+             : m.D == 128 ? "ewma_train_kernel<128>" : "ewma_train_kernel<256>";
         dim3 block(kEwmaWPC * 32), grid((p.P + kEwmaWPC - 1) / kEwmaWPC);
         switch (m.D) {
             case 16: ewma_train_kernel<16><<<grid, block, 0, st>>>(m, p); break;
@@ -789,6 +793,7 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
         }
     } else if (int nt = lstm_kernel_choice(m, p.P)) {
         *err = launch_lstm_tc3(m, p, nt, st);
+        kn = nt == 2 ? "lstm_tc3_train_kernel<2,2>" : "lstm_tc3_train_kernel<1,2>";
         return 1;
     } else {
         dim3 block(kLstmWPC * 32), grid((p.P + kLstmWPC - 1) / kLstmWPC);
@@ -797,11 +802,13 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
             *err = cudaFuncSetAttribute(lstm_train_kernel<32, kLstmWPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (*err != cudaSuccess) return 0;
             lstm_train_kernel<32, kLstmWPC><<<grid, block, smem, st>>>(m, p);
+            kn = "lstm_train_kernel<32,8>";
         } else if (m.D == 16) {
             constexpr size_t smem = lstm_smem_bytes<16, kLstmWPC>();
             *err = cudaFuncSetAttribute(lstm_train_kernel<16, kLstmWPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (*err != cudaSuccess) return 0;
             lstm_train_kernel<16, kLstmWPC><<<grid, block, smem, st>>>(m, p);
+            kn = "lstm_train_kernel<16,8>";
         } else if (m.D == 64 || m.D == 128 || m.D == 256) {
             constexpr int WPCW = 4;
             dim3 blockw(WPCW * 32), gridw((p.P + WPCW - 1) / WPCW);
@@ -809,6 +816,7 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
             if (m.D == 64) lstm_wide_train_kernel<64, WPCW><<<gridw, blockw, smem, st>>>(m, p);
             else if (m.D == 128) lstm_wide_train_kernel<128, WPCW><<<gridw, blockw, smem, st>>>(m, p);
             else lstm_wide_train_kernel<256, WPCW><<<gridw, blockw, smem, st>>>(m, p);
+            kn = m.D == 64 ? "lstm_wide_train_kernel<64,4>" : m.D == 128 ? "lstm_wide_train_kernel<128,4>" : "lstm_wide_train_kernel<256,4>";
         } else { *err = cudaErrorInvalidValue; return 0; }
     }
     *err = cudaGetLastError();

@@ -27,7 +27,7 @@ def stream_csr(rng, num_users, num_items, length, zipf=False):
 
 
 def make_pair(pkg, O, kind, num_items, T, D, loss="hinge", optimizer="adagrad", variant="normal", lr=0.05, l2=1e-4,
-              epochs=1, threads=1, parallelism="asynchronous", seed=bytes(range(1, 17)), scale=None):
+              epochs=1, threads=1, parallelism="asynchronous", seed=bytes(range(1, 17)), scale=None, exact=False):
     """Builds the GPU model and an oracle model holding bit-identical parameters, optimizer state and rng."""
     H = pkg.lstm.Hyperparameters if kind == "lstm" else pkg.ewma.Hyperparameters
     h = (H(num_items, T).embedding_dim(D).learning_rate(lr).l2_penalty(l2).loss(LOSSES[loss])
@@ -35,6 +35,8 @@ def make_pair(pkg, O, kind, num_items, T, D, loss="hinge", optimizer="adagrad", 
          .from_seed(seed))
     if kind == "lstm":
         h = h.lstm_variant(VARIANTS[variant])
+    if exact:
+        h = h.exact_arithmetic()
     gm = h.build()
     om = O.OracleModel(kind, num_items, T, embedding_dim=D, learning_rate=lr, l2_penalty=l2, lstm_variant=variant,
                        loss=loss, optimizer=optimizer, parallelism=parallelism, num_threads=threads,

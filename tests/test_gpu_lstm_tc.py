@@ -27,29 +27,43 @@ def _adagrad(w, G, g, lr, l2):
     return w.astype(np.float32), G.astype(np.float32)
 
 
-# every generation of the tile kernel stays under the same parity gate (SBR_LSTM_TC, kernels_train.cu:launch_train):
-# "3" = default (2 threads per sequence, L2-atomic Adagrad), "34" = 4 threads per sequence, "2" = thread per sequence
-# with the prefetch pipeline, "1" = the first tile kernel
-GENERATIONS = [("3", 128, "normal"), ("3", 256, "normal"), ("3", 256, "coupled"), ("34", 256, "normal"), ("2", 256, "normal"),
-               ("2", 128, "coupled"), ("1", 256, "normal")]
+def _adam(w, m, v, g, lr, l2, t):
+    g = np.float32(g) + w * np.float32(l2)
+    m = np.float32(0.9) * m + np.float32(0.1) * g
+    v = np.float32(0.999) * v + np.float32(0.001) * g * g
+    c1, c2 = np.float32(1.0 - 0.9 ** t), np.float32(1.0 - 0.999 ** t)
+    w = w - np.float32(lr) * (m / c1) / (np.sqrt(v / c2) + np.float32(1e-8))
+    return w.astype(np.float32), m.astype(np.float32), v.astype(np.float32)
 
 
-@pytest.mark.parametrize("gen,P,variant", GENERATIONS)
-def test_one_round_matches_oracle_gradients(pkg, oracle, monkeypatch, gen, P, variant):
-    monkeypatch.setenv("SBR_LSTM_TC", gen)
+# The benchmarked kernel on the benchmarked loss: (partitions, variant, loss, optimizer).  WARP and hinge take decisions
+# on scores (accept / reject a candidate, hinge active or not); a sequence in which the oracle's margin of any decision is
+# closer to 0 than DECISION_BAND could legitimately decide differently under tf32 products and is left out of the
+# element-wise comparison (its rows are still required to be finite) -- at most a few per cent of the sequences.
+CASES = [(128, "normal", "bpr", "adagrad"), (256, "normal", "bpr", "adagrad"), (256, "coupled", "bpr", "adagrad"),
+         (256, "normal", "warp", "adagrad"), (128, "coupled", "warp", "adagrad"), (256, "normal", "hinge", "adagrad"),
+         (256, "normal", "warp", "adam"), (256, "normal", "bpr", "adam")]
+DECISION_BAND = 5e-3
+
+
+@pytest.mark.parametrize("P,variant,loss,optimizer", CASES)
+def test_one_round_matches_oracle_gradients(pkg, oracle, P, variant, loss, optimizer):
     N, T, D, lr, l2 = 60000, 8, 32, 0.05, 1e-3
+    adam = optimizer == "adam"
     ptr = (np.arange(P + 1) * T).astype(np.uint64)
     ids = (1000 + np.arange(P * T)).astype(np.uint64)          # user u owns items 1000+8u .. 1000+8u+7
-    gm, om = make_pair(pkg, oracle, "lstm", N, T, D, loss="bpr", optimizer="adagrad", variant=variant, lr=lr, l2=l2,
+    gm, om = make_pair(pkg, oracle, "lstm", N, T, D, loss=loss, optimizer=optimizer, variant=variant, lr=lr, l2=l2,
                        epochs=1, threads=P, scale=0.3)
     rs = np.random.default_rng(9)
     gm.set_parameter("lstm_weights", (rs.uniform(-0.3, 0.3, 2 * D * 4 * D)).astype(np.float32))
     gm.set_parameter("lstm_biases", (rs.uniform(-0.3, 0.3, 4 * D)).astype(np.float32))
+    # second-moment state 1 (Adagrad G / Adam v): updates are smooth in the gradient (~ lr * g resp. lr * g / 31.6 at t = 1)
+    slot = ".s2" if adam else ".s1"
     for n in ("item_embeddings", "item_biases", "lstm_weights", "lstm_biases"):
-        gm.set_parameter(n + ".s1", np.ones(len(gm.get_parameter(n)), dtype=np.float32))  # Adagrad G = 1: updates ~ lr * g
+        gm.set_parameter(n + slot, np.ones(len(gm.get_parameter(n)), dtype=np.float32))
     for n in om.param_names():
         om.param(n)[:] = gm.get_parameter(n)
-        om.param(n + ".s1")[:] = 1.0
+        om.param(n + slot)[:] = 1.0
     E0, b0 = om.param("item_embeddings").reshape(N, D).copy(), om.param("item_biases").copy()
     W0 = np.concatenate([om.param("lstm_weights"), om.param("lstm_biases")]).copy()
 
@@ -65,12 +79,14 @@ def test_one_round_matches_oracle_gradients(pkg, oracle, monkeypatch, gen, P, va
 
     data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
     gm.fit(data)
-    assert gm.last_fit_stats()["partitions"] == P
+    st = gm.last_fit_stats()
+    assert st["partitions"] == P and st["kernel_launches"] == 1
 
-    E, GE = E0.copy(), np.ones_like(E0)
-    b, Gb = b0.copy(), np.ones_like(b0)
+    E, SE1, SE2 = E0.copy(), (np.zeros_like(E0) if adam else np.ones_like(E0)), np.ones_like(E0)
+    b, Sb1, Sb2 = b0.copy(), (np.zeros_like(b0) if adam else np.ones_like(b0)), np.ones_like(b0)
     dense_sum = np.zeros_like(W0)
-    touched = {}
+    touched, shaky = {}, set()
+    tries_hist = np.zeros(6, dtype=np.int64)
     for p in range(P):
         sq = int(order[p])
         seq = ids[sq * T:(sq + 1) * T]
@@ -79,50 +95,84 @@ def test_one_round_matches_oracle_gradients(pkg, oracle, monkeypatch, gen, P, va
         rows, grads, brows, bgrads = om.last_sparse_grads()
         for rrow in set(rows.tolist()) | set(brows.tolist()):
             touched.setdefault(rrow, set()).add(p)
+        # decision margins of this sequence at the initial parameters (sequence_model.rs:47-68; lstm.rs:318)
+        if loss != "bpr":
+            for t in range(T - 1):
+                h = om.user_representation(seq[:t + 1])[1]
+                pos = float(h @ E0[int(seq[t + 1])] + b0[int(seq[t + 1])])
+                chosen = None
+                for j in range(5 if loss == "warp" else 1):
+                    cand = int(L.sbo_draw_item(keys[p], 0, t, j, N))
+                    margin = 1.0 - pos + float(h @ E0[cand] + b0[cand])
+                    if abs(margin) < DECISION_BAND:
+                        shaky.add(p)
+                    chosen = cand
+                    if margin > 0.0:
+                        break
+                assert chosen == int(negs[t])        # the negatives the oracle trained on are the ones replayed here
+                tries_hist[j + 1] += 1
+        tstep = p + 1                                 # Adam step counter of partition p in round 0
         for rrow, gr in zip(rows.tolist(), grads):
-            E[rrow], GE[rrow] = _adagrad(E[rrow], GE[rrow], gr, lr, l2)
+            if adam:
+                E[rrow], SE1[rrow], SE2[rrow] = _adam(E[rrow], SE1[rrow], SE2[rrow], gr, lr, l2, tstep)
+            else:
+                E[rrow], SE1[rrow] = _adagrad(E[rrow], SE1[rrow], gr, lr, l2)
         for rrow, gr in zip(brows.tolist(), bgrads.tolist()):
-            wv, gv = _adagrad(b[rrow:rrow + 1], Gb[rrow:rrow + 1], gr, lr, l2)
-            b[rrow], Gb[rrow] = wv[0], gv[0]
-    W1, _ = _adagrad(W0, np.ones_like(W0), dense_sum, lr, l2)
+            if adam:
+                wv, mv, vv = _adam(b[rrow:rrow + 1], Sb1[rrow:rrow + 1], Sb2[rrow:rrow + 1], gr, lr, l2, tstep)
+                b[rrow], Sb1[rrow], Sb2[rrow] = wv[0], mv[0], vv[0]
+            else:
+                wv, gv = _adagrad(b[rrow:rrow + 1], Sb1[rrow:rrow + 1], gr, lr, l2)
+                b[rrow], Sb1[rrow] = wv[0], gv[0]
+    if loss == "warp":
+        assert tries_hist[2:].sum() > 0.05 * tries_hist.sum(), tries_hist   # rejections do happen: the WARP loop is exercised
+    assert len(shaky) <= 0.06 * P, (len(shaky), P)
+    if adam:
+        W1, _, _ = _adam(W0, np.zeros_like(W0), np.ones_like(W0), dense_sum, lr, l2, 1)
+    else:
+        W1, _ = _adagrad(W0, np.ones_like(W0), dense_sum, lr, l2)
 
-    clean = np.array(sorted(k for k, v in touched.items() if len(v) == 1), dtype=np.int64)
-    assert len(clean) > 0.9 * len(touched)
+    clean = np.array(sorted(k for k, v in touched.items() if len(v) == 1 and not (v & shaky)), dtype=np.int64)
+    assert len(clean) > 0.85 * len(touched)
     gE = gm.get_parameter("item_embeddings").reshape(N, D)
     gb = gm.get_parameter("item_biases")
     gW = np.concatenate([gm.get_parameter("lstm_weights"), gm.get_parameter("lstm_biases")])
-    assert np.abs(E[clean] - E0[clean]).mean() > 5e-4            # the comparison is not vacuous
-    assert np.abs(gE[clean] - E[clean]).max() <= 4e-4, np.abs(gE[clean] - E[clean]).max()
-    assert np.abs(gb[clean] - b[clean]).max() <= 4e-4
-    dW = np.abs(W1 - W0)
-    err = np.abs(gW - W1)
-    assert dW.mean() > 1e-3
-    assert err.max() <= 1e-3 and err.mean() <= 1e-4, (err.max(), err.mean(), dW.mean())
+    assert np.all(np.isfinite(gE)) and np.all(np.isfinite(gb)) and np.all(np.isfinite(gW))
+    tol = 4e-4
+    assert np.abs(E[clean] - E0[clean]).mean() > (2e-5 if adam else 5e-4)   # the comparison is not vacuous
+    assert np.abs(gE[clean] - E[clean]).max() <= tol, np.abs(gE[clean] - E[clean]).max()
+    assert np.abs(gb[clean] - b[clean]).max() <= tol
+    # optimizer state of the clean rows (Adagrad G / Adam m, v) as well
+    g1 = gm.get_parameter("item_embeddings.s1").reshape(N, D)
+    assert np.abs(g1[clean] - SE1[clean]).max() <= (2e-3 if not adam else tol)
+    if adam:
+        g2 = gm.get_parameter("item_embeddings.s2").reshape(N, D)
+        assert np.abs(g2[clean] - SE2[clean]).max() <= tol
+    if not shaky:                     # the dense gradient sums over every sequence, shaky ones included
+        dW = np.abs(W1 - W0)
+        err = np.abs(gW - W1)
+        assert dW.mean() > (2e-5 if adam else 1e-3)
+        assert err.max() <= 1e-3 and err.mean() <= 1e-4, (err.max(), err.mean(), dW.mean())
     untouched = np.setdiff1d(np.arange(N), np.array(sorted(touched), dtype=np.int64))
-    assert np.array_equal(gE[untouched], E0[untouched])          # rows nobody named are bit-identical
+    if not shaky:
+        assert np.array_equal(gE[untouched], E0[untouched])      # rows nobody named are bit-identical
 
 
 @pytest.mark.parametrize("loss,optimizer,lr", [("bpr", "adagrad", 0.05), ("warp", "adagrad", 0.05), ("hinge", "adam", 0.002)])
 def test_tile_kernel_learns_like_the_exact_path(pkg, oracle, loss, optimizer, lr):
     """Statistical parity on an ML-100K-shaped stream: per-epoch losses of the tile kernel (256 partitions) track the
     exact FFMA kernel run with the same partition count, and parameters stay finite."""
-    import os
     rng = np.random.default_rng(5)
     N, T, D = 1683, 32, 32
     ptr, ids = stream_csr(rng, 16384, N, 32)
     losses = {}
     for kern in ("ffma", "tc"):
-        if kern == "ffma":
-            os.environ["SBR_LSTM_KERNEL"] = "ffma"
-        else:
-            os.environ.pop("SBR_LSTM_KERNEL", None)
         gm, _ = make_pair(pkg, oracle, "lstm", N, T, D, loss=loss, optimizer=optimizer, variant="normal", lr=lr,
-                          l2=1e-4, epochs=1, threads=256)
+                          l2=1e-4, epochs=1, threads=256, exact=(kern == "ffma"))
         data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
         losses[kern] = [gm.fit(data) / 256 for _ in range(6)]
         for n in ("item_embeddings", "item_biases", "lstm_weights", "lstm_biases"):
             assert np.all(np.isfinite(gm.get_parameter(n))), (kern, n)
-    os.environ.pop("SBR_LSTM_KERNEL", None)
     a, b = np.array(losses["ffma"]), np.array(losses["tc"])
     assert b[-1] < b[0]
     # Adam's normalised steps amplify the bf16 / tf32 rounding of the first gradients: wider band for that case

@@ -4,13 +4,16 @@ plus independent checks (finite differences, published SipHash vector) where the
 No GPU needed.  The oracle is "parity unpinned" at the wyrm arithmetic boundary (the reference is Rust and cannot be
 built here); what can be pinned is pinned here.
 """
+import json
 import os
+import sys
 
 import numpy as np
 import pytest
 
 import oracle_lib as O
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_CSV = "/root/reference/data.csv"
 
 
@@ -248,43 +251,68 @@ def test_optimizer_semantics_adagrad_duplicates_not_merged():
 
 
 # ------------------------------------------------------------------------------- statistical pins (MRR floors) --
-def _split_ml100k(ml100k):
-    up = ml100k["user_ptr"].astype(np.int64)
-    users = np.repeat(np.arange(944), np.diff(up)).astype(np.uint64)
-    items, ts = ml100k["item_ids"].astype(np.uint64), ml100k["timestamps"].astype(np.uint64)
-    is_train, rng = O.user_based_split(users, bytes([42] * 16), 0.2)  # lstm.rs:428-430
-    tr = O.compress(users[is_train], items[is_train], ts[is_train], 944)
-    te = O.compress(users[~is_train], items[~is_train], ts[~is_train], 944)
-    return tr, te
+# The reference pins its models with MRR floors on ML-100K (lstm.rs:450-520, ewma.rs:463-507): ONE run each, on the split
+# user_based_split(0.2) of XorShift [42;16], with the model seeded from the same rng, so every floor is a single draw set
+# just under the value the author saw.  One oracle run has a spread of ~0.012 over model seeds (190 test users), so a
+# single seed cannot say whether the oracle clears a floor.  profiles/tools/oracle_mrr_seeds.py runs every recipe over 16
+# model seeds (profiles/r2_oracle_mrr_floors.json); here the first SEEDS of them are re-run live (deterministic with one
+# thread), must reproduce the committed values, and their MEAN must clear the reference's own, un-loosened floor.
+SEEDS = 6
+
+
+def _floor_job(args):
+    sys.path.insert(0, os.path.join(ROOT, "profiles", "tools"))
+    import oracle_mrr_seeds as S
+    return S.one(args)
+
+
+def _run_recipe(name):
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "profiles", "tools"))
+    import oracle_mrr_seeds as S
+    recipe = [r for r in S.RECIPES if r[0] == name][0]
+    jobs = [(recipe, s, 128, 10, False, False) for s in range(SEEDS)]
+    with mp.get_context("fork").Pool(min(SEEDS, os.cpu_count() or 1)) as pool:
+        res = pool.map(_floor_job, jobs, chunksize=1)
+    vals = np.array([m for _, _, m in sorted(res, key=lambda r: r[1])])
+    with open(os.path.join(ROOT, "profiles", "r2_oracle_mrr_floors.json")) as f:
+        committed = json.load(f)["results"][name]
+    return vals, committed
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize("loss,floor", [("hinge", 0.091), ("warp", 0.089)])
-def test_ewma_mrr_floor(ml100k, loss, floor):
-    """ewma.rs:463-507: seq 128, dim 32, lr 0.16, l2 4e-4, Adagrad, 10 epochs; test MRR > 0.11 / 0.14 by default and
-    > 0.091 / 0.089 under MKL_CBWR=AVX (the CI setting).  Statistical pin: the oracle (different rng streams, exact
-    libm) must clear the CI floors."""
-    tr, te = _split_ml100k(ml100k)
-    m = O.OracleModel("ewma", 1683, 128, embedding_dim=32, learning_rate=0.16, l2_penalty=0.0004, loss=loss,
-                      optimizer="adagrad", num_epochs=10, num_threads=1)
-    rc, _ = m.fit(tr[0], tr[1])
-    assert rc == 0
-    rc, mrr = m.mrr_score(te[0], te[1])
-    assert rc == 0 and mrr > floor, mrr
+@pytest.mark.parametrize("name", ["lstm_hinge_1thread", "lstm_warp_1thread"])
+def test_lstm_mrr_floor(name):
+    """lstm.rs:450-472 (hinge, floor 0.081) and lstm.rs:498-520 (WARP, floor 0.10): seq 128, dim 32, lr 0.16, l2 4e-4,
+    LSTMVariant::Normal, Adagrad, 10 epochs, 1 thread.  The mean over model seeds clears the DEFAULT floor."""
+    vals, committed = _run_recipe(name)
+    assert np.allclose(vals, committed["values"][:SEEDS], atol=1e-6), (vals, committed["values"][:SEEDS])
+    assert vals.mean() > committed["floor_default"], (vals.mean(), committed["floor_default"])
+    assert committed["mean"] > committed["floor_default"]
 
 
 @pytest.mark.slow
-def test_lstm_mrr_floor(ml100k):
-    """lstm.rs:450-472: same recipe, LSTMVariant::Normal, hinge, 1 thread: test MRR > 0.081 (0.091 AVX).
-    The floors themselves move by 0.01 with the BLAS mode and the test set has ~180 users (s.e. ~0.015), so the pin
-    is: within 0.02 of the default floor."""
-    tr, te = _split_ml100k(ml100k)
-    m = O.OracleModel("lstm", 1683, 128, embedding_dim=32, learning_rate=0.16, l2_penalty=0.0004,
-                      lstm_variant="normal", loss="hinge", optimizer="adagrad", num_epochs=10, num_threads=1)
-    rc, _ = m.fit(tr[0], tr[1])
-    assert rc == 0
-    rc, mrr = m.mrr_score(te[0], te[1])
-    assert rc == 0 and mrr > 0.081 - 0.02, mrr
+@pytest.mark.parametrize("name", ["ewma_hinge_1thread", "ewma_warp_1thread"])
+def test_ewma_mrr_floor(name):
+    """ewma.rs:463-507: same recipe; floors 0.11 / 0.14 by default, 0.091 / 0.089 under MKL_CBWR=AVX (the CI setting).
+    Every seed clears the CI floor.  Against the default floors the 16-seed means are 0.1089 +- 0.0023 (hinge, floor 0.11:
+    inside one standard error) and 0.1253 +- 0.0019 (WARP, floor 0.14: best seed 0.1375) -- recorded, not asserted;
+    DESIGN.md 5 discusses it."""
+    vals, committed = _run_recipe(name)
+    assert np.allclose(vals, committed["values"][:SEEDS], atol=1e-6), (vals, committed["values"][:SEEDS])
+    assert vals.min() > committed["floor_avx"], (vals, committed["floor_avx"])
+    assert committed["mean"] > committed["floor_default"] - 0.016
+
+
+def test_committed_floor_runs_are_consistent():
+    """profiles/r2_oracle_mrr_floors.json (16 model seeds per recipe on the reference's split): every LSTM mean clears its
+    default floor, including the 2-thread Hogwild recipe lstm.rs:474-496 (not re-run here: it is not deterministic)."""
+    with open(os.path.join(ROOT, "profiles", "r2_oracle_mrr_floors.json")) as f:
+        r = json.load(f)["results"]
+    for name in ("lstm_hinge_1thread", "lstm_hinge_2threads", "lstm_warp_1thread"):
+        assert len(r[name]["values"]) >= 16 and r[name]["mean"] > r[name]["floor_default"], name
+    for name in ("ewma_hinge_1thread", "ewma_warp_1thread"):
+        assert r[name]["seeds_above_avx_floor"] == len(r[name]["values"]), name
 
 
 def test_multithread_modes_run(ml100k):
