@@ -264,8 +264,8 @@ struct sbr_model {
     float* scratch_cache = nullptr; size_t scratch_cap = 0; bool scratch_busy = false;  // grow-only activation scratch
     ~sbr_model() {
         for (int i = 0; i < 8; ++i) {
-            if (own[i]) { if (dev.Es[i]) cudaFree(dev.Es[i]); if (dev.Bs[i]) cudaFree(dev.Bs[i]); }
-            else { if (dev.Es[i]) cudaIpcCloseMemHandle(dev.Es[i]); if (dev.Bs[i]) cudaIpcCloseMemHandle(dev.Bs[i]); }
+            if (own[i]) { if (dev.Es[i]) cudaFree(dev.Es[i]); }
+            else if (dev.Es[i]) cudaIpcCloseMemHandle(dev.Es[i]);
         }
         if (dev.dense && dev.dense != own_dense) cudaIpcCloseMemHandle(dev.dense);
         if (own_dense) cudaFree(own_dense);
@@ -616,8 +616,7 @@ sbr_status sbr_hyper_build(sbr_hyperparameters* hp, sbr_model** out) {
     for (int g = 0; g < G; ++g) {
         if (h.shard_world > 1 && g != h.shard_rank) continue;   // peers' shards are mapped by sbr_model_ipc_attach
         const size_t rows = ((size_t)d.N + G - 1 - g) / G;       // ids g, g+G, g+2G, ...
-        if ((e = cudaMalloc(&d.Es[g], std::max<size_t>(rows, 1) * d.S * d.D * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc item table");
-        if ((e = cudaMalloc(&d.Bs[g], std::max<size_t>(rows, 1) * sizeof(float4))) != cudaSuccess) return bail(e, "cudaMalloc bias table");
+        if ((e = cudaMalloc(&d.Es[g], std::max<size_t>(rows, 1) * rec_floats(d) * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc item table");
         m->own[g] = true;
     }
     if ((e = cudaMalloc(&d.dense, 3 * d.ndense * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc dense parameters");
@@ -686,7 +685,7 @@ void sbr_dist_finalize(void) {
     g_rank = 0; g_world = 1;
 }
 
-size_t sbr_model_ipc_handle_size(void) { return 3 * sizeof(cudaIpcMemHandle_t); }
+size_t sbr_model_ipc_handle_size(void) { return 2 * sizeof(cudaIpcMemHandle_t); }
 
 sbr_status sbr_model_ipc_export(const sbr_model* m, void* out) {
     if (!m || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
@@ -696,8 +695,7 @@ sbr_status sbr_model_ipc_export(const sbr_model* m, void* out) {
     if (m->h.shard_world <= 1) return fail(SBR_ERR_INVALID_ARGUMENT, "model was not built with sbr_hyper_shard");
     cudaIpcMemHandle_t* hs = reinterpret_cast<cudaIpcMemHandle_t*>(out);
     CU(cudaIpcGetMemHandle(&hs[0], m->dev.Es[r]));
-    CU(cudaIpcGetMemHandle(&hs[1], m->dev.Bs[r]));
-    CU(cudaIpcGetMemHandle(&hs[2], m->own_dense));
+    CU(cudaIpcGetMemHandle(&hs[1], m->own_dense));
     return SBR_OK;
 }
 
@@ -712,16 +710,15 @@ sbr_status sbr_model_ipc_attach(sbr_model* m, const void* all_handles) {
     const cudaIpcMemHandle_t* hs = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);
     for (int g = 0; g < W; ++g) {
         if (g == r) continue;
-        void* pe = nullptr; void* pb = nullptr;
-        CU(cudaIpcOpenMemHandle(&pe, hs[3 * g + 0], cudaIpcMemLazyEnablePeerAccess));
-        CU(cudaIpcOpenMemHandle(&pb, hs[3 * g + 1], cudaIpcMemLazyEnablePeerAccess));
-        m->dev.Es[g] = static_cast<float*>(pe); m->dev.Bs[g] = static_cast<float4*>(pb);
+        void* pe = nullptr;
+        CU(cudaIpcOpenMemHandle(&pe, hs[2 * g + 0], cudaIpcMemLazyEnablePeerAccess));
+        m->dev.Es[g] = static_cast<float*>(pe);
     }
     // Asynchronous: the dense parameters (LSTM weights / alpha) live on rank 0 and everyone updates them Hogwild.
     // Synchronous: every rank keeps its own replica (identical on all ranks: same all-reduced gradient every round).
     if (r != 0 && m->h.parallelism != SBR_PARALLELISM_SYNCHRONOUS) {
         void* pd = nullptr;
-        CU(cudaIpcOpenMemHandle(&pd, hs[2], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&pd, hs[1], cudaIpcMemLazyEnablePeerAccess));
         m->dev.dense = static_cast<float*>(pd);
     }
     m->attached = true;

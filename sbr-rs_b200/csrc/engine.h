@@ -15,12 +15,13 @@ struct ModelDev {
     int model, variant, loss, opt;
     uint32_t N;
     int D, T;
-    int S;           // floats-vectors per item row record: 2 (w,G) Adagrad, 3 (w,m,v) Adam
+    int S;           // float-vectors per item record: 2 (w,G) Adagrad, 3 (w,m,v) Adam
     // Item table, row-sharded by item id: shard = id & gmask, local row = id >> gshift (G = gmask+1 is 1, 2, 4 or 8).
-    // With G == 1 everything is in Es[0] / Bs[0].  With G > 1 a shard is either local memory (virtual shards, tests)
+    // With G == 1 everything is in Es[0].  With G > 1 a shard is either local memory (virtual shards, tests)
     // or a peer GPU's memory mapped through CUDA IPC (one process per GPU; loads/stores travel over NVLink).
-    float* Es[8];    // [rows of shard][S][D]
-    float4* Bs[8];   // [rows of shard] {b, s1, s2, pad}
+    // One RECORD per item: {b, b.s1, b.s2, pad} (16 bytes) | w[D] | s1[D] | (s2[D])  --  4 + S*D floats, contiguous, so
+    // that ONE bulk copy / bulk reduce-add moves everything a sparse optimizer visit of the item touches.
+    float* Es[8];    // [rows of shard][4 + S*D]
     uint32_t gmask;
     int gshift;
     int hbm_resident; // table + state larger than L2: kernels prefetch rows a few timesteps ahead
@@ -52,10 +53,17 @@ struct PlanDev {
 };
 
 #ifdef __CUDACC__
+__host__ __device__ __forceinline__ size_t rec_floats(const ModelDev& m) { return 4 + (size_t)m.S * m.D; }
+// the record's vectors: item_rec() points at w (s1 at + D, s2 at + 2 D); bias_rec() at the {b, s1, s2, pad} quad in front of it
 __device__ __forceinline__ float* item_rec(const ModelDev& m, uint32_t id) {
-    return m.Es[id & m.gmask] + (size_t)(id >> m.gshift) * ((size_t)m.S * m.D);
+    return m.Es[id & m.gmask] + (size_t)(id >> m.gshift) * rec_floats(m) + 4;
 }
-__device__ __forceinline__ float4* bias_rec(const ModelDev& m, uint32_t id) { return m.Bs[id & m.gmask] + (id >> m.gshift); }
+__device__ __forceinline__ float4* bias_rec(const ModelDev& m, uint32_t id) {
+    return reinterpret_cast<float4*>(m.Es[id & m.gmask] + (size_t)(id >> m.gshift) * rec_floats(m));
+}
+// local row r of this process's own shard
+__device__ __forceinline__ float* shard_item_rec(const ModelDev& m, int shard, uint32_t r) { return m.Es[shard] + (size_t)r * rec_floats(m) + 4; }
+__device__ __forceinline__ float4* shard_bias_rec(const ModelDev& m, int shard, uint32_t r) { return reinterpret_cast<float4*>(m.Es[shard] + (size_t)r * rec_floats(m)); }
 #endif
 
 // launchers (kernels_train.cu / kernels_infer.cu); all enqueue on `st` and return the launch count
@@ -65,6 +73,8 @@ int train_auto_partitions(const ModelDev& m, int num_sms);
 bool train_supported(const ModelDev& m, const char** why);
 int lstm_kernel_choice(const ModelDev& m, uint32_t P);
 cudaError_t launch_lstm_tc3(const ModelDev& m, const PlanDev& p, int nt, cudaStream_t st);
+cudaError_t launch_lstm_tile(const ModelDev& m, const PlanDev& p, cudaStream_t st);
+int lstm_tile_tiles_per_cta(const ModelDev& m, uint32_t P);
 
 // round-synchronous engine (sync_engine.cu)
 struct SyncBuffers;

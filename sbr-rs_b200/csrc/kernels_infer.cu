@@ -30,7 +30,6 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(ModelDev m, const uint
 template <int D>
 __device__ __forceinline__ void ewma_represent(const ModelDev& m, const uint32_t* ids, int n, int lane, float* out) {
     constexpr int V = VecOf<D>::V;
-    const size_t RS = (size_t)m.S * D;
     float al[V], a[V], s[V], x[V];
     row_load_cg<D>(m.dense, lane, al);
 #pragma unroll

@@ -107,8 +107,8 @@ struct Slice { uint8_t* p; uint32_t gs; };
 struct Table { float* e0; float* const* es; uint32_t stride, gmask; int gshift; };
 template <bool FLAT>
 __device__ __forceinline__ float* trec(const Table& tb, uint32_t id) {
-    if (FLAT) return tb.e0 + (size_t)id * tb.stride;
-    return tb.es[id & tb.gmask] + (size_t)(id >> tb.gshift) * tb.stride;
+    if (FLAT) return tb.e0 + (size_t)id * tb.stride + 4;
+    return tb.es[id & tb.gmask] + (size_t)(id >> tb.gshift) * tb.stride + 4;
 }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128 * NT * DS, 1) lstm_tc3_train_kernel(ModelD
     const int T = m.T;
     float** es_s = reinterpret_cast<float**>(smem + OFF_MISC + 64);         // [8] shard base pointers of the item table
     if (tid < 8) es_s[tid] = m.Es[tid];
-    Table tb; tb.e0 = m.Es[0]; tb.es = es_s; tb.stride = (uint32_t)(m.S * m.D); tb.gmask = m.gmask; tb.gshift = m.gshift;
+    Table tb; tb.e0 = m.Es[0]; tb.es = es_s; tb.stride = (uint32_t)rec_floats(m); tb.gmask = m.gmask; tb.gshift = m.gshift;
 
     auto tile_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(tile + 1), "n"(TT) : "memory"); };
     auto quad_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(3 + tile * 4 + q), "n"(32 * DS) : "memory"); };

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 
 
+#include <cstdlib>
+
 #include "engine.h"
 
 namespace sbr {
@@ -44,7 +46,6 @@ template <int D>
 __device__ __forceinline__ void score_and_sample(const ModelDev& m, int lane, const float (&h)[VecOf<D>::V], uint32_t out,
                                                  uint64_t key, uint64_t step, uint32_t t, uint32_t range, float (&p)[VecOf<D>::V],
                                                  float (&q)[VecOf<D>::V], uint32_t& neg, float& pos, float& ngs) {
-    const size_t RS = (size_t)m.S * D;
     row_load_cg<D>(item_rec(m, out), lane, p);
     pos = warp_dot<D>(h, p) + __ldcg(reinterpret_cast<const float*>(bias_rec(m, out)));
     const int tries = m.loss == 2 ? 5 : 1;
@@ -100,7 +101,6 @@ __global__ void __launch_bounds__(256) ewma_train_kernel(ModelDev m, PlanDev pl)
     const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= pl.P) return;
     const int T = m.T;
-    const size_t RS = (size_t)m.S * D;
     float* ws = pl.scratch + (size_t)p * pl.scratch_stride;
     float* S_ = ws; float* X_ = ws + (size_t)T * D; float* DQ = ws + 2 * (size_t)T * D;
     float* G_ = ws + 3 * (size_t)T * D; uint32_t* NEG = reinterpret_cast<uint32_t*>(G_ + T);
@@ -331,7 +331,6 @@ __global__ void __launch_bounds__(WPC * 32) lstm_train_kernel(ModelDev m, PlanDe
     const uint32_t p = blockIdx.x * WPC + warp;
     const bool live = p < pl.P;
     const int T = m.T;
-    const size_t RS = (size_t)m.S * D;
     const size_t nd = m.ndense;
     const bool coupled = m.variant == 1;
     float* myz = zbuf + warp * NK;
@@ -792,8 +791,13 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
             default: *err = cudaErrorInvalidValue; return 0;
         }
     } else if (int nt = lstm_kernel_choice(m, p.P)) {
-        *err = launch_lstm_tc3(m, p, nt, st);
-        kn = nt == 2 ? "lstm_tc3_train_kernel<2,2>" : "lstm_tc3_train_kernel<1,2>";
+        if (getenv("SBR_TILE_OLD")) {   // TEMPORARY A/B switch while the new tile kernel is validated
+            *err = launch_lstm_tc3(m, p, nt, st);
+            kn = nt == 2 ? "lstm_tc3_train_kernel<2,2>" : "lstm_tc3_train_kernel<1,2>";
+            return 1;
+        }
+        *err = launch_lstm_tile(m, p, st);
+        kn = m.opt == 1 ? "lstm_tile_train_kernel<1,3>" : lstm_tile_tiles_per_cta(m, p.P) == 2 ? "lstm_tile_train_kernel<2,2>" : "lstm_tile_train_kernel<1,2>";
         return 1;
     } else {
         dim3 block(kLstmWPC * 32), grid((p.P + kLstmWPC - 1) / kLstmWPC);

@@ -110,13 +110,12 @@ __global__ void __launch_bounds__(256) sync_gather_kernel(ModelDev m, int self, 
                                                           float* __restrict__ out_rows, float* __restrict__ out_bias) {
     constexpr int V = VecOf<D>::V;
     const int lane = threadIdx.x & 31;
-    const size_t RS = (size_t)m.S * D;
     for (size_t j = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += (size_t)gridDim.x * (blockDim.x >> 5)) {
         const uint32_t r = rows[j];
         float w[V];
-        row_load_cg<D>(m.Es[self] + (size_t)r * RS, lane, w);
+        row_load_cg<D>(shard_item_rec(m, self, r), lane, w);
         vec_store<D>(out_rows + j * D, lane, w);
-        if (lane == 0) out_bias[j] = __ldcg(reinterpret_cast<const float*>(m.Bs[self] + r));
+        if (lane == 0) out_bias[j] = __ldcg(reinterpret_cast<const float*>(shard_bias_rec(m, self, r)));
     }
 }
 
@@ -213,7 +212,6 @@ __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, c
                                                          const float* __restrict__ bgrads, size_t n, OptCfg o) {
     constexpr int V = VecOf<D>::V;
     const int lane = threadIdx.x & 31;
-    const size_t RS = (size_t)m.S * D;
     for (size_t j = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += (size_t)gridDim.x * (blockDim.x >> 5)) {
         const uint32_t r = (uint32_t)(keys[j] >> 32);
         if (j > 0 && (uint32_t)(keys[j - 1] >> 32) == r) continue;   // not the first entry of its row
@@ -221,10 +219,10 @@ __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, c
             const uint32_t src = vals[e];
             float g[V];
             vec_load<D>(grads + (size_t)src * D, lane, g);
-            update_row<D>(m.Es[self] + (size_t)r * RS, lane, g, o);
+            update_row<D>(shard_item_rec(m, self, r), lane, g, o);
             if (lane == 0) {
                 const float bg = bgrads[src];
-                if (bg == bg) update_bias(m.Bs[self] + r, bg, o);
+                if (bg == bg) update_bias(shard_bias_rec(m, self, r), bg, o);
             }
             __syncwarp();
         }
