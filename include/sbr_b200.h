@@ -223,7 +223,7 @@ typedef struct {
     double train_kernel_ms;  /* CUDA-event time of the training kernel(s) on the engine's stream */
     double total_device_ms;  /* CUDA-event time from first H2D to last D2H */
     double host_prepare_ms;  /* sub-sequence build + shuffle + partitioning on the host */
-    char kernel[64];         /* name of the training kernel the plan ran on (e.g. "lstm_tc3_train_kernel<2,2>") */
+    char kernel[64];         /* name of the training kernel the plan ran on (e.g. "lstm_tile_train_kernel<2,2>") */
 } sbr_fit_stats;
 
 /* Host-only test hook: the schedule fit() builds from a CSR -- sequence_model.rs:76-84: chunks of every user

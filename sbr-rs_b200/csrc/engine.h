@@ -72,7 +72,6 @@ size_t train_scratch_floats_per_warp(const ModelDev& m);
 int train_auto_partitions(const ModelDev& m, int num_sms);
 bool train_supported(const ModelDev& m, const char** why);
 int lstm_kernel_choice(const ModelDev& m, uint32_t P);
-cudaError_t launch_lstm_tc3(const ModelDev& m, const PlanDev& p, int nt, cudaStream_t st);
 cudaError_t launch_lstm_tile(const ModelDev& m, const PlanDev& p, cudaStream_t st);
 int lstm_tile_tiles_per_cta(const ModelDev& m, uint32_t P);
 

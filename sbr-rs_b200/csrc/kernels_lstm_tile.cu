@@ -59,6 +59,38 @@ __device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.app
 __device__ __forceinline__ float sigm(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tnh(float x) { return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(-2.8853900817779268f * x)), -1.0f); }
 
+// ---- packed fp32 pairs (FFMA2 / FMUL2 / FADD2: one issue slot for two lanes of a vector) ----
+__device__ __forceinline__ float2 fma2(const float2& a, const float2& b, const float2& c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(const float2& a, const float2& b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 add2(const float2& a, const float2& b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 sigm2(const float2& x) {
+    const float2 t = mul2(x, splat2(-1.4426950408889634f));
+    const float2 e = add2(make_float2(ex2_approx(t.x), ex2_approx(t.y)), splat2(1.0f));
+    return make_float2(rcp_approx(e.x), rcp_approx(e.y));
+}
+__device__ __forceinline__ float2 tnh2(const float2& x) {
+    const float2 t = mul2(x, splat2(-2.8853900817779268f));
+    const float2 e = add2(make_float2(ex2_approx(t.x), ex2_approx(t.y)), splat2(1.0f));
+    return fma2(make_float2(rcp_approx(e.x), rcp_approx(e.y)), splat2(2.0f), splat2(-1.0f));
+}
+__device__ __forceinline__ float2 bf2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+
 __device__ __forceinline__ uint32_t word_of(const uint4& u, int pr) { return pr == 0 ? u.x : pr == 1 ? u.y : pr == 2 ? u.z : u.w; }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
@@ -105,6 +137,15 @@ __device__ __forceinline__ void apply4(float4& w, float4& s, float4& v, const fl
     } else {
         adam1(w.x, s.x, v.x, sign * g.x, o); adam1(w.y, s.y, v.y, sign * g.y, o); adam1(w.z, s.z, v.z, sign * g.z, o); adam1(w.w, s.w, v.w, sign * g.w, o);
     }
+}
+// Adagrad on a pair of elements, as deltas: g' = g + l2 w ; dG = g'^2 ; dw = -lr g' / sqrt(G + dG)   (w, G are updated too)
+__device__ __forceinline__ void adagrad2(float2& w, float2& G, const float2& g, const OptC& o, float2& dw, float2& dG) {
+    const float2 gg = fma2(w, splat2(o.l2), g);
+    dG = mul2(gg, gg);
+    G = add2(G, dG);
+    const float2 rs = make_float2(rsqrt_approx(fmaxf(G.x, 1e-20f)), rsqrt_approx(fmaxf(G.y, 1e-20f)));
+    dw = mul2(mul2(gg, splat2(-o.lr)), rs);
+    w = add2(w, dw);
 }
 __device__ __forceinline__ float4 sub4(const float4& a, const float4& b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 
@@ -258,7 +299,8 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
     uint64_t key = 0; uint32_t* ord = nullptr;
     uint64_t step = pl.step_ctr[live ? p : 0];
     if (live) { key = pl.keys[p]; ord = pl.order + (size_t)p * pl.n; }
-    OptC o; o.lr = m.lr; o.l2 = m.l2; o.adam = m.opt == 1; o.c1 = 1.0f; o.c2 = 1.0f;
+    constexpr bool ADAM = S == 3;   // 400-byte records <=> Adam
+    OptC o; o.lr = m.lr; o.l2 = m.l2; o.adam = ADAM ? 1 : 0; o.c1 = 1.0f; o.c2 = 1.0f;
     const int tries = m.loss == 2 ? 5 : 1;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -276,7 +318,7 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
         }
         quad_bar();   // the other owner reads the shuffled order (same SM: visible after the barrier)
         for (uint32_t it = 0; it < pl.n; ++it, ++step) {
-            if (o.adam) {
+            if (ADAM) {
                 const float tt_ = (float)(pl.adam_t0 + step * pl.P + (live ? p : 0) + 1);
                 o.c1 = 1.0f - powf(0.9f, tt_); o.c2 = 1.0f - powf(0.999f, tt_);
             }
@@ -303,10 +345,10 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
             uint32_t idB = 0, idC = 0;   // ids[t+1], ids[t+2] travel in registers of the lead owner (ids has Tn + 1 entries)
             if (Tmax > 0) {
                 // x_0 = E[ids[0]]: one record copy {bias quad | w} into the P slot
-                if (lead) {
-                    uint32_t idA = 0;
-                    if (Tn > 0) { idA = __ldg(ids); idB = __ldg(ids + 1); }
-                    if (Tn > 1) idC = __ldg(ids + 2);
+                uint32_t idA = 0;
+                if (Tn > 0) { idA = __ldg(ids); idB = __ldg(ids + 1); }
+                if (Tn > 1) idC = __ldg(ids + 2);
+                if (!lead) {
                     bulk_load(pslot, trec<FLAT>(tb, idA), PSLOT, qbar);
                     if (lane == 0) mbar_arrive_expect_tx(qbar, 32 * PSLOT);
                 }
@@ -324,12 +366,13 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
             }
             for (int t = 0; t < Tmax; ++t) {
                 const bool act = t < Tn;
+                // Bulk copies take uniform-register operands: per-lane addresses run as a 32-iteration loop in the issuing warp.
+                // The two loads of a forward timestep are issued by the SECOND owner's warp, the reduce-adds (and the chain
+                // record's load behind its reduce-add, same slot) by the lead owner's -- an even split of those loops.
                 uint32_t out = 0, c0 = 0, idD = 0;
-                if (lead) {
-                    out = act ? idB : 0u;
-                    if (t + 3 <= Tn) idD = __ldg(ids + t + 3);
-                    c0 = draw_item(key, step, (uint32_t)t, 0u, pl.neg_range);
-                }
+                out = act ? idB : 0u;
+                if (t + 3 <= Tn) idD = __ldg(ids + t + 3);
+                c0 = draw_item(key, step, (uint32_t)t, 0u, pl.neg_range);
                 fence_async_smem();          // Z_t (written by every owner during the previous step) -> tensor-core proxy
                 tc_fence_before_sync();
                 tile_bar();
@@ -342,8 +385,7 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
                 }
                 // the records this timestep scores against: the target row {bias, w} and the first candidate (full record: it
                 // becomes the negative's optimizer visit); the slots were released by the previous step
-                if (lead) {
-                    bulk_wait_read();        // the previous step's reduce-add has read the slot
+                if (!lead) {                 // (the lead owner waited for its reduce-add to have read the slot before the tile barrier)
                     bulk_load(pslot, trec<FLAT>(tb, out), PSLOT, qbar);
                     bulk_load(rslot, trec<FLAT>(tb, c0), REC, qbar);
                     if (lane == 0) mbar_arrive_expect_tx(qbar, 32 * (PSLOT + REC));
@@ -357,15 +399,17 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
                     tmem_ld8(tcs + b * 8, pc);   // c_{t-1}
                     tmem_ld8x4(tbase + gb * 8, tbase + 32 + gb * 8, tbase + 64 + gb * 8, tbase + 96 + gb * 8, pf, pi, pg, po);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float f = sigm(pf[j]);
-                        const float ig = coupled ? 1.0f - f : sigm(pi[j]);
-                        const float gg = tnh(pg[j]);
-                        const float og = sigm(po[j]);
-                        const float cn = f * pc[j] + ig * gg;
-                        const float tcn = tnh(cn);
-                        h[b * 8 + j] = act ? og * tcn : 0.0f;
-                        pf[j] = f; pi[j] = ig; pg[j] = gg; po[j] = og; pc[j] = cn; ptc[j] = tcn;
+                    for (int j = 0; j < 8; j += 2) {   // two hidden units per packed instruction
+                        const float2 f = sigm2(make_float2(pf[j], pf[j + 1]));
+                        const float2 ig = coupled ? fma2(f, splat2(-1.0f), splat2(1.0f)) : sigm2(make_float2(pi[j], pi[j + 1]));
+                        const float2 gg = tnh2(make_float2(pg[j], pg[j + 1]));
+                        const float2 og = sigm2(make_float2(po[j], po[j + 1]));
+                        const float2 cn = fma2(f, make_float2(pc[j], pc[j + 1]), mul2(ig, gg));
+                        const float2 tcn = tnh2(cn);
+                        const float2 hn = mul2(og, tcn);
+                        h[b * 8 + j] = act ? hn.x : 0.0f; h[b * 8 + j + 1] = act ? hn.y : 0.0f;
+                        pf[j] = f.x; pf[j + 1] = f.y; pi[j] = ig.x; pi[j + 1] = ig.y; pg[j] = gg.x; pg[j + 1] = gg.y;
+                        po[j] = og.x; po[j + 1] = og.y; pc[j] = cn.x; pc[j + 1] = cn.y; ptc[j] = tcn.x; ptc[j + 1] = tcn.y;
                     }
                     tmem_st8(tcs + b * 8, pc);   // (finished sequences carry garbage from here on: never read again as a live value)
                     if (act) {
@@ -415,11 +459,11 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
                 // decisions are bit-identical in both owners, so both warps of a quad take the same path
                 for (int j = 1; j < tries; ++j) {
                     if (__all_sync(kFull, done)) break;
-                    if (lead) {
+                    {
                         const uint32_t cj = draw_item(key, step, (uint32_t)t, (uint32_t)j, pl.neg_range);
-                        if (!done) { neg = cj; bulk_load(rslot, trec<FLAT>(tb, cj), REC, qbar); }
+                        if (!done) { neg = cj; if (!lead) bulk_load(rslot, trec<FLAT>(tb, cj), REC, qbar); }
                         const uint32_t n = __popc(__ballot_sync(kFull, !done));
-                        if (lane == 0) mbar_arrive_expect_tx(qbar, n * REC);
+                        if (!lead && lane == 0) mbar_arrive_expect_tx(qbar, n * REC);
                     }
                     rec_wait();
                     score();
@@ -444,22 +488,32 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
                     if (act) {
                         *sb8(t, AHB, gb) = hp;
                         if (t + 1 < Tn) *sb8(t + 1, AX, gb) = xp;
-                        const float4 da = make_float4(g * (qa.x - pa.x), g * (qa.y - pa.y), g * (qa.z - pa.z), g * (qa.w - pa.w));
-                        const float4 db_ = make_float4(g * (qb.x - pb.x), g * (qb.y - pb.y), g * (qb.z - pb.z), g * (qb.w - pb.w));
-                        *sb8(t, ADQ, gb) = pack8(da, db_);
+                        const float2 g2 = splat2(g), ng2 = splat2(-g);   // g (q - p) = g q - g p
+                        const float2 d0 = fma2(g2, make_float2(qa.x, qa.y), mul2(ng2, make_float2(pa.x, pa.y)));
+                        const float2 d1 = fma2(g2, make_float2(qa.z, qa.w), mul2(ng2, make_float2(pa.z, pa.w)));
+                        const float2 d2 = fma2(g2, make_float2(qb.x, qb.y), mul2(ng2, make_float2(pb.x, pb.y)));
+                        const float2 d3 = fma2(g2, make_float2(qb.z, qb.w), mul2(ng2, make_float2(pb.z, pb.w)));
+                        *sb8(t, ADQ, gb) = make_uint4(pack2(d0.x, d0.y), pack2(d1.x, d1.y), pack2(d2.x, d2.y), pack2(d3.x, d3.y));
                     }
                 }
                 // ---- the negative's visit, in its slot: E[neg_t] += step(+g h_t), b[neg_t] += step(+g) ----
                 if (act) {
 #pragma unroll
                     for (int cc = 0; cc < NCH; ++cc) {
-                        float4 w = qv[cc], s1 = rs_ld(1, cc), s2 = zero4;
-                        if (S == 3) s2 = rs_ld(2, cc);
-                        const float4 w0 = w, s10 = s1, s20 = s2;
-                        const float4 gh = make_float4(g * h[4 * cc], g * h[4 * cc + 1], g * h[4 * cc + 2], g * h[4 * cc + 3]);
-                        apply4(w, s1, s2, gh, 1.0f, o);
-                        rs_st(0, cc, sub4(w, w0)); rs_st(1, cc, sub4(s1, s10));
-                        if (S == 3) rs_st(2, cc, sub4(s2, s20));
+                        if (!ADAM) {
+                            const float4 G4 = rs_ld(1, cc);
+                            float2 wa = make_float2(qv[cc].x, qv[cc].y), wb_ = make_float2(qv[cc].z, qv[cc].w);
+                            float2 Ga = make_float2(G4.x, G4.y), Gb = make_float2(G4.z, G4.w), dwa, dwb, dGa, dGb;
+                            adagrad2(wa, Ga, mul2(splat2(g), make_float2(h[4 * cc], h[4 * cc + 1])), o, dwa, dGa);
+                            adagrad2(wb_, Gb, mul2(splat2(g), make_float2(h[4 * cc + 2], h[4 * cc + 3])), o, dwb, dGb);
+                            rs_st(0, cc, make_float4(dwa.x, dwa.y, dwb.x, dwb.y)); rs_st(1, cc, make_float4(dGa.x, dGa.y, dGb.x, dGb.y));
+                        } else {
+                            float4 w = qv[cc], s1 = rs_ld(1, cc), s2 = rs_ld(2, cc);
+                            const float4 w0 = w, s10 = s1, s20 = s2;
+                            const float4 gh = make_float4(g * h[4 * cc], g * h[4 * cc + 1], g * h[4 * cc + 2], g * h[4 * cc + 3]);
+                            apply4(w, s1, s2, gh, 1.0f, o);
+                            rs_st(0, cc, sub4(w, w0)); rs_st(1, cc, sub4(s1, s10)); rs_st(2, cc, sub4(s2, s20));
+                        }
                     }
                     if (lead) {
                         float4 bq = *reinterpret_cast<const float4*>(rslot_g);
@@ -470,10 +524,12 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
                 }
                 fence_async_smem();      // the deltas in the slot (and Z_{t+1}) -> async proxy
                 quad_bar();              // both owners have written their halves / are done reading the slots
-                if (lead && act) { bulk_reduce_add(trec<FLAT>(tb, neg), rslot, REC); bulk_commit(); }
+                if (lead) {
+                    if (act) { bulk_reduce_add(trec<FLAT>(tb, neg), rslot, REC); bulk_commit(); }
+                    bulk_wait_read();    // the slot is free again before this owner reaches the next tile barrier
+                }
                 idB = idC; idC = idD;
             }
-            if (lead) bulk_wait_read();
 
             // =========================== backward ===========================
             // dz of timestep t+1 (dh_t in TMEM columns 0..31, dx_{t+1} in 32..63) is consumed straight from TMEM inside
@@ -534,34 +590,35 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
                             dxv[2 * b + 1] = make_float4(__uint_as_float(rb[4]), __uint_as_float(rb[5]), __uint_as_float(rb[6]), __uint_as_float(rb[7]));
                         }
                         // gradient of the target row: g h_t (h_t from its bf16 copy)
-                        ghv[2 * b] = make_float4(g * bf_lo(cur.h.x), g * bf_hi(cur.h.x), g * bf_lo(cur.h.y), g * bf_hi(cur.h.y));
-                        ghv[2 * b + 1] = make_float4(g * bf_lo(cur.h.z), g * bf_hi(cur.h.z), g * bf_lo(cur.h.w), g * bf_hi(cur.h.w));
+                        {   // (stored negated: the entry of the target row is -g h_t)
+                            const float2 ng2 = splat2(-g);
+                            const float2 a0_ = mul2(ng2, bf2(cur.h.x)), a1_ = mul2(ng2, bf2(cur.h.y)), a2_ = mul2(ng2, bf2(cur.h.z)), a3_ = mul2(ng2, bf2(cur.h.w));
+                            ghv[2 * b] = make_float4(a0_.x, a0_.y, a1_.x, a1_.y);
+                            ghv[2 * b + 1] = make_float4(a2_.x, a2_.y, a3_.x, a3_.y);
+                        }
                         uint32_t wdf[4], wdi[4], wdg[4], wdo[4];
 #pragma unroll
                         for (int pr = 0; pr < 4; ++pr) {   // two hidden units at a time, straight from / to packed bf16 words
                             const uint32_t uf = word_of(cur.f, pr), ui = word_of(cur.i, pr), ug = word_of(cur.g, pr), uo = word_of(cur.o, pr);
                             const uint32_t uq = word_of(cur.q, pr), ucp = word_of(cur.cp, pr), utc = word_of(cur.tc, pr);
-                            float rdf[2], rdi[2], rdg[2], rdo[2];
-#pragma unroll
-                            for (int k = 0; k < 2; ++k) {
-                                const int e = 2 * pr + k;
-                                const float f_ = k ? bf_hi(uf) : bf_lo(uf), i_ = k ? bf_hi(ui) : bf_lo(ui), g_ = k ? bf_hi(ug) : bf_lo(ug);
-                                const float o_ = k ? bf_hi(uo) : bf_lo(uo), q_ = k ? bf_hi(uq) : bf_lo(uq);
-                                const float cp_ = k ? bf_hi(ucp) : bf_lo(ucp), tcv = k ? bf_hi(utc) : bf_lo(utc);
-                                const float dh = dhv[e] + q_;
-                                const float d_o = dh * tcv;
-                                const float dc = dcv[e] + dh * o_ * (1.0f - tcv * tcv);
-                                float d_f = dc * cp_, d_i = dc * g_;
-                                const float d_g = dc * i_;
-                                dcv[e] = act ? dc * f_ : 0.0f;
-                                if (coupled) { d_f -= d_i; d_i = 0.0f; }
-                                rdf[k] = d_f * f_ * (1.0f - f_);
-                                rdi[k] = coupled ? 0.0f : d_i * i_ * (1.0f - i_);
-                                rdg[k] = d_g * (1.0f - g_ * g_);
-                                rdo[k] = d_o * o_ * (1.0f - o_);
-                            }
-                            wdf[pr] = pack2(rdf[0], rdf[1]); wdi[pr] = pack2(rdi[0], rdi[1]);
-                            wdg[pr] = pack2(rdg[0], rdg[1]); wdo[pr] = pack2(rdo[0], rdo[1]);
+                            const float2 f_ = bf2(uf), i_ = bf2(ui), g_ = bf2(ug), o_ = bf2(uo), q_ = bf2(uq), cp_ = bf2(ucp), tcv = bf2(utc);
+                            const int e = 2 * pr;
+                            const float2 one = splat2(1.0f);
+                            const float2 dh = add2(make_float2(dhv[e], dhv[e + 1]), q_);
+                            const float2 d_o = mul2(dh, tcv);
+                            const float2 dc = fma2(mul2(dh, o_), fma2(mul2(tcv, splat2(-1.0f)), tcv, one), make_float2(dcv[e], dcv[e + 1]));
+                            float2 d_f = mul2(dc, cp_), d_i = mul2(dc, g_);
+                            const float2 d_g = mul2(dc, i_);
+                            const float2 dcn = mul2(dc, f_);
+                            dcv[e] = act ? dcn.x : 0.0f; dcv[e + 1] = act ? dcn.y : 0.0f;
+                            if (coupled) { d_f = fma2(d_i, splat2(-1.0f), d_f); d_i = splat2(0.0f); }
+                            const float2 nf = mul2(f_, splat2(-1.0f)), ni = mul2(i_, splat2(-1.0f)), ng = mul2(g_, splat2(-1.0f)), no = mul2(o_, splat2(-1.0f));
+                            const float2 rdf = mul2(d_f, fma2(nf, f_, f_));                 // d_f f (1 - f)
+                            const float2 rdi = coupled ? splat2(0.0f) : mul2(d_i, fma2(ni, i_, i_));
+                            const float2 rdg = mul2(d_g, fma2(ng, g_, one));                // d_g (1 - g^2)
+                            const float2 rdo = mul2(d_o, fma2(no, o_, o_));
+                            wdf[pr] = pack2(rdf.x, rdf.y); wdi[pr] = pack2(rdi.x, rdi.y);
+                            wdg[pr] = pack2(rdg.x, rdg.y); wdo[pr] = pack2(rdo.x, rdo.y);
                         }
                         *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 0 + gb, 16)) = make_uint4(wdf[0], wdf[1], wdf[2], wdf[3]);
                         *reinterpret_cast<uint4*>(Db + tile_chunk_off(r, 4 + gb, 16)) = make_uint4(wdi[0], wdi[1], wdi[2], wdi[3]);
@@ -604,13 +661,26 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
                 if (visit) {
 #pragma unroll
                     for (int cc = 0; cc < NCH; ++cc) {
-                        float4 w = rs_ld(0, cc), s1 = rs_ld(1, cc), s2 = zero4;
-                        if (S == 3) s2 = rs_ld(2, cc);
-                        const float4 w0 = w, s10 = s1, s20 = s2;
-                        if (has_dx) apply4(w, s1, s2, dxv[cc], 1.0f, o);
-                        if (act) apply4(w, s1, s2, ghv[cc], -1.0f, o);
-                        rs_st(0, cc, sub4(w, w0)); rs_st(1, cc, sub4(s1, s10));
-                        if (S == 3) rs_st(2, cc, sub4(s2, s20));
+                        if (!ADAM) {
+                            const float4 w4 = rs_ld(0, cc), G4 = rs_ld(1, cc);
+                            float2 wa = make_float2(w4.x, w4.y), wb_ = make_float2(w4.z, w4.w), Ga = make_float2(G4.x, G4.y), Gb = make_float2(G4.z, G4.w);
+                            float2 dwa = splat2(0.0f), dwb = dwa, dGa = dwa, dGb = dwa, t0, t1;
+                            if (has_dx) {
+                                adagrad2(wa, Ga, make_float2(dxv[cc].x, dxv[cc].y), o, dwa, dGa);
+                                adagrad2(wb_, Gb, make_float2(dxv[cc].z, dxv[cc].w), o, dwb, dGb);
+                            }
+                            if (act) {   // ghv holds -g h_t
+                                adagrad2(wa, Ga, make_float2(ghv[cc].x, ghv[cc].y), o, t0, t1); dwa = add2(dwa, t0); dGa = add2(dGa, t1);
+                                adagrad2(wb_, Gb, make_float2(ghv[cc].z, ghv[cc].w), o, t0, t1); dwb = add2(dwb, t0); dGb = add2(dGb, t1);
+                            }
+                            rs_st(0, cc, make_float4(dwa.x, dwa.y, dwb.x, dwb.y)); rs_st(1, cc, make_float4(dGa.x, dGa.y, dGb.x, dGb.y));
+                        } else {
+                            float4 w = rs_ld(0, cc), s1 = rs_ld(1, cc), s2 = rs_ld(2, cc);
+                            const float4 w0 = w, s10 = s1, s20 = s2;
+                            if (has_dx) apply4(w, s1, s2, dxv[cc], 1.0f, o);
+                            if (act) apply4(w, s1, s2, ghv[cc], 1.0f, o);   // ghv holds -g h_t
+                            rs_st(0, cc, sub4(w, w0)); rs_st(1, cc, sub4(s1, s10)); rs_st(2, cc, sub4(s2, s20));
+                        }
                     }
                     if (lead) {
                         float4 bq = *reinterpret_cast<const float4*>(rslot_g);

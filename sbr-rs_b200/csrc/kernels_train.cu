@@ -7,8 +7,6 @@
 #include <cuda_runtime.h>
 
 
-#include <cstdlib>
-
 #include "engine.h"
 
 namespace sbr {
@@ -537,7 +535,7 @@ __global__ void __launch_bounds__(WPC * 32) lstm_train_kernel(ModelDev m, PlanDe
 // from L2 (ld.cg: they are Hogwild-shared) as coalesced V-float vectors, three passes per timestep (gates, dz, dW).
 // The dense optimizer step is applied per sequence by the warp itself, rows of W at a time, exactly like the
 // reference (one optimizer.step per sub-sequence, sequence_model.rs:163-169).  Correct and parity-tested; the
-// tensor-core tile kernel (kernels_lstm_tc.cu) is the fast path and currently covers D = 32 only.
+// tensor-core tile kernel (kernels_lstm_tile.cu) is the fast path and currently covers D = 32 only.
 // scratch per warp: [T][8][D] = x,h,c,f,i,g,o,dq ; then G[T], NEG[T]
 // =====================================================================================================
 template <int D, int WPC>
@@ -766,11 +764,10 @@ int train_auto_partitions(const ModelDev& m, int num_sms) {
     return num_sms * per_sm;
 }
 
-// which LSTM kernel a plan runs on: 0 = FFMA (exact fp32, warp per partition), 1 / 2 = tensor-core tiles per CTA.
-// The tile kernel takes whole tiles of 128 partitions; sbr_hyper_exact_arithmetic(h, 1) keeps the exact path.
+// which LSTM kernel a plan runs on: 0 = FFMA (exact fp32, warp per partition), 1 = the tensor-core tile kernel
+// (kernels_lstm_tile.cu), which takes whole tiles of 128 partitions; sbr_hyper_exact_arithmetic(h, 1) keeps the exact path.
 int lstm_kernel_choice(const ModelDev& m, uint32_t P) {
-    if (m.exact || m.model != MODEL_LSTM || m.D != 32 || P < 128 || P % 128 != 0) return 0;
-    return P % 256 == 0 ? 2 : 1;
+    return (m.exact || m.model != MODEL_LSTM || m.D != 32 || P < 128 || P % 128 != 0) ? 0 : 1;
 }
 
 int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t st, cudaError_t* err, const char** kernel_name) {
@@ -790,12 +787,7 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
             case 256: ewma_train_kernel<256><<<grid, block, 0, st>>>(m, p); break;
             default: *err = cudaErrorInvalidValue; return 0;
         }
-    } else if (int nt = lstm_kernel_choice(m, p.P)) {
-        if (getenv("SBR_TILE_OLD")) {   // TEMPORARY A/B switch while the new tile kernel is validated
-            *err = launch_lstm_tc3(m, p, nt, st);
-            kn = nt == 2 ? "lstm_tc3_train_kernel<2,2>" : "lstm_tc3_train_kernel<1,2>";
-            return 1;
-        }
+    } else if (lstm_kernel_choice(m, p.P)) {
         *err = launch_lstm_tile(m, p, st);
         kn = m.opt == 1 ? "lstm_tile_train_kernel<1,3>" : lstm_tile_tiles_per_cta(m, p.P) == 2 ? "lstm_tile_train_kernel<2,2>" : "lstm_tile_train_kernel<1,2>";
         return 1;
