@@ -1076,7 +1076,7 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
         P = std::min(autoP, std::max<size_t>(1, nsub / 16));
         // the LSTM tile kernels take whole tiles of 128 partitions (2 tiles per CTA): round down so that real data
         // (nsub / 16 is almost never a multiple of 128) still runs on them
-        if (m->dev.model == MODEL_LSTM && m->dev.D == 32) { if (P >= 256) P -= P % 256; else if (P >= 128) P = 128; }
+        if (m->dev.D == 32 && !m->dev.exact) { if (P >= 256) P -= P % 256; else if (P >= 128) P = 128; }
     }
     if (P > nsub) return fail(SBR_ERR_INVALID_ARGUMENT, "num_threads exceeds the number of sub-sequences (the reference panics in chunks_mut(0))");
     const size_t n = nsub / P;  // :91, remainder dropped by the zip at :94-96

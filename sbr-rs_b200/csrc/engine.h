@@ -73,6 +73,8 @@ int train_auto_partitions(const ModelDev& m, int num_sms);
 bool train_supported(const ModelDev& m, const char** why);
 int lstm_kernel_choice(const ModelDev& m, uint32_t P);
 cudaError_t launch_lstm_tile(const ModelDev& m, const PlanDev& p, cudaStream_t st);
+cudaError_t launch_ewma_tile(const ModelDev& m, const PlanDev& p, cudaStream_t st);
+int ewma_tile_tiles_per_cta(const ModelDev& m, uint32_t P);
 int lstm_tile_tiles_per_cta(const ModelDev& m, uint32_t P);
 
 // round-synchronous engine (sync_engine.cu)

@@ -11,8 +11,10 @@
 //     272-byte record {bias quad | w[32] | G[32]} of an item into the sequence's own shared-memory slot (mbarrier
 //     completion), and `cp.reduce.async.bulk.global.shared.add.f32` adds the optimizer step {db, dGb | dw[32] | dG[32]}
 //     back into the live table at L2 -- no per-16-byte loads, atomics, shuffles or pointer arithmetic in the SM, no lost
-//     updates between the thousands of partitions that hit the same hot rows (Adagrad's accumulator is additive; for Adam
-//     the deltas of m and v are added).  Slot strides (144 / 272 / 400 bytes) are = 16 mod 128: lane-per-row 16-byte
+//     updates between the thousands of partitions that hit the same hot rows (Adagrad's accumulator is additive).  Adam
+//     records go back with a plain bulk STORE of the new {b, m, v | w | m | v}: its moments are decaying averages, and
+//     m += 0.1 (g - m_seen) summed over K concurrent visitors of a hot row diverges for K > 20 -- Hogwild overwrites as in
+//     the reference cannot.  Slot strides (144 / 272 / 400 bytes) are = 16 mod 128: lane-per-row 16-byte
 //     accesses are bank-conflict free.
 //   * the three contractions of a timestep run on the tensor cores from shared-memory operand tiles with TMEM
 //     accumulators (tc_tile.cuh: tcgen05.mma kind::f16 on bf16 operands, fp32 accumulation):
@@ -109,6 +111,9 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, ui
 }
 __device__ __forceinline__ void bulk_reduce_add(void* dst, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -509,23 +514,25 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
                             rs_st(0, cc, make_float4(dwa.x, dwa.y, dwb.x, dwb.y)); rs_st(1, cc, make_float4(dGa.x, dGa.y, dGb.x, dGb.y));
                         } else {
                             float4 w = qv[cc], s1 = rs_ld(1, cc), s2 = rs_ld(2, cc);
-                            const float4 w0 = w, s10 = s1, s20 = s2;
                             const float4 gh = make_float4(g * h[4 * cc], g * h[4 * cc + 1], g * h[4 * cc + 2], g * h[4 * cc + 3]);
                             apply4(w, s1, s2, gh, 1.0f, o);
-                            rs_st(0, cc, sub4(w, w0)); rs_st(1, cc, sub4(s1, s10)); rs_st(2, cc, sub4(s2, s20));
+                            rs_st(0, cc, w); rs_st(1, cc, s1); rs_st(2, cc, s2);   // Adam: new values, plain store (below)
                         }
                     }
                     if (lead) {
                         float4 bq = *reinterpret_cast<const float4*>(rslot_g);
                         const float4 b0 = bq;
                         if (!o.adam) adagrad1(bq.x, bq.y, g, o); else adam1(bq.x, bq.y, bq.z, g, o);
-                        *reinterpret_cast<float4*>(rslot_g) = make_float4(bq.x - b0.x, bq.y - b0.y, bq.z - b0.z, 0.0f);
+                        *reinterpret_cast<float4*>(rslot_g) = ADAM ? bq : make_float4(bq.x - b0.x, bq.y - b0.y, 0.0f, 0.0f);
                     }
                 }
                 fence_async_smem();      // the deltas in the slot (and Z_{t+1}) -> async proxy
                 quad_bar();              // both owners have written their halves / are done reading the slots
                 if (lead) {
-                    if (act) { bulk_reduce_add(trec<FLAT>(tb, neg), rslot, REC); bulk_commit(); }
+                    if (act) {
+                        if (ADAM) bulk_store(trec<FLAT>(tb, neg), rslot, REC); else bulk_reduce_add(trec<FLAT>(tb, neg), rslot, REC);
+                        bulk_commit();
+                    }
                     bulk_wait_read();    // the slot is free again before this owner reaches the next tile barrier
                 }
                 idB = idC; idC = idD;
@@ -676,23 +683,25 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
                             rs_st(0, cc, make_float4(dwa.x, dwa.y, dwb.x, dwb.y)); rs_st(1, cc, make_float4(dGa.x, dGa.y, dGb.x, dGb.y));
                         } else {
                             float4 w = rs_ld(0, cc), s1 = rs_ld(1, cc), s2 = rs_ld(2, cc);
-                            const float4 w0 = w, s10 = s1, s20 = s2;
                             if (has_dx) apply4(w, s1, s2, dxv[cc], 1.0f, o);
                             if (act) apply4(w, s1, s2, ghv[cc], 1.0f, o);   // ghv holds -g h_t
-                            rs_st(0, cc, sub4(w, w0)); rs_st(1, cc, sub4(s1, s10)); rs_st(2, cc, sub4(s2, s20));
+                            rs_st(0, cc, w); rs_st(1, cc, s1); rs_st(2, cc, s2);
                         }
                     }
                     if (lead) {
                         float4 bq = *reinterpret_cast<const float4*>(rslot_g);
                         const float4 b0 = bq;
                         if (act) { if (!o.adam) adagrad1(bq.x, bq.y, -g, o); else adam1(bq.x, bq.y, bq.z, -g, o); }
-                        *reinterpret_cast<float4*>(rslot_g) = make_float4(bq.x - b0.x, bq.y - b0.y, bq.z - b0.z, 0.0f);
+                        *reinterpret_cast<float4*>(rslot_g) = ADAM ? bq : make_float4(bq.x - b0.x, bq.y - b0.y, 0.0f, 0.0f);
                     }
                 }
                 fence_async_smem();
                 quad_bar();
                 if (lead) {
-                    if (visit) { bulk_reduce_add(trec<FLAT>(tb, row_c), rslot, REC); bulk_commit(); }
+                    if (visit) {
+                        if (ADAM) bulk_store(trec<FLAT>(tb, row_c), rslot, REC); else bulk_reduce_add(trec<FLAT>(tb, row_c), rslot, REC);
+                        bulk_commit();
+                    }
                     if (t >= 0) {   // the next (earlier) timestep's record, as soon as the reduce-add has read the slot
                         row_c = chain_id(t - 1);
                         bulk_wait_read();

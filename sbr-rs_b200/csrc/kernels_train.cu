@@ -758,7 +758,7 @@ size_t train_scratch_floats_per_warp(const ModelDev& m) {
 
 int train_auto_partitions(const ModelDev& m, int num_sms) {
     // EWMA / FFMA LSTM: resident warps per SM (registers / shared memory); tensor-core LSTM: 2 tiles of 128 per SM
-    if (m.model == MODEL_LSTM && m.D == 32) return num_sms * 256;
+    if (m.D == 32 && !m.exact) return num_sms * (m.opt == 1 ? 128 : 256);   // tile kernels: 2 x 128 partitions per SM (Adam records: 1 x 128)
     if (m.model == MODEL_LSTM && m.D > 32) return num_sms * 8;
     int per_sm = m.model == MODEL_EWMA ? (m.D <= 64 ? 32 : 16) : 16;
     return num_sms * per_sm;
@@ -775,7 +775,12 @@ int launch_train(const ModelDev& m, const PlanDev& p, int num_sms, cudaStream_t 
     *err = cudaSuccess;
     const char* dummy; const char*& kn = kernel_name ? *kernel_name : dummy;
     kn = "";
-    if (m.model == MODEL_EWMA) {
+    if (m.model == MODEL_EWMA && !m.exact && m.D == 32 && p.P >= 128 && p.P % 128 == 0) {
+        // many partitions: thread-per-half-sequence kernel with bulk-copied records (kernels_ewma_tile.cu)
+        *err = launch_ewma_tile(m, p, st);
+        kn = m.opt == 1 ? "ewma_tile_train_kernel<1,3>" : ewma_tile_tiles_per_cta(m, p.P) == 2 ? "ewma_tile_train_kernel<2,2>" : "ewma_tile_train_kernel<1,2>";
+        return 1;
+    } else if (m.model == MODEL_EWMA) {
         kn = m.D == 16 ? "ewma_train_kernel<16>" : m.D == 32 ? "ewma_train_kernel<32>" : m.D == 64 ? "ewma_train_kernel<64>"
              : m.D == 128 ? "ewma_train_kernel<128>" : "ewma_train_kernel<256>";
         dim3 block(kEwmaWPC * 32), grid((p.P + kEwmaWPC - 1) / kEwmaWPC);
