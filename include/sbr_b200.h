@@ -222,7 +222,8 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
     double train_kernel_ms;  /* CUDA-event time of the training kernel(s) on the engine's stream */
     double total_device_ms;  /* CUDA-event time from first H2D to last D2H */
-    double host_prepare_ms;  /* sub-sequence build + shuffle + partitioning on the host */
+    double host_prepare_ms;  /* host side of the schedule: counting sub-sequences, master shuffle, partition rngs */
+    double upload_ms;        /* wall time of the id-stream upload (narrow + H2D), which runs beside host_prepare; 0 if resident */
     char kernel[64];         /* name of the training kernel the plan ran on (e.g. "lstm_tile_train_kernel<2,2>") */
 } sbr_fit_stats;
 
@@ -232,11 +233,22 @@ typedef struct {
 sbr_status sbr_host_schedule(const sbr_compressed* c, size_t max_sequence_length, uint32_t rng_state[4], uint64_t* starts,
                              uint32_t* lens, uint32_t* order, size_t cap, size_t* nsub);
 
+/* Host-only test hook: what fit() does with the master rng (sequence_model.rs:84,97) -- Fisher-Yates over the indices
+ * 0..nsub, then one [u8; 16] seed per partition (the negative-sampler key of a partition is the first 8 bytes of its seed) --
+ * with the rng stream produced by `threads` host threads (xorshift128 jump-ahead; threads <= 1: the plain loop).
+ * order: nsub entries; keys: partitions entries (may be NULL when partitions == 0); rng_state in/out. */
+sbr_status sbr_host_master_schedule(uint32_t rng_state[4], size_t nsub, size_t partitions, size_t threads, uint32_t* order, uint64_t* keys);
+
 /* Split of sbr_model_fit into "stage once" + "run": create does sequence_model.rs:74-98 (sub-sequences, shuffle,
  * partitions, per-partition rngs) and puts everything in HBM; run does :100-175 for num_epochs epochs. */
 sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* interactions, sbr_fit_plan** out);
 sbr_status sbr_fit_plan_run(sbr_fit_plan* p, float* loss_out);
 sbr_status sbr_fit_plan_stats(const sbr_fit_plan* p, sbr_fit_stats* out);
+/* Test hook: the schedule the plan staged in HBM -- sub-sequences built by the DEVICE chunker in user order (starts, lens:
+ * nsub entries) and the master-shuffled partition-major order (partitions * per-partition entries; epochs permute it in
+ * place).  With cap < *nsub only the counts are returned.  tests/test_gpu_data_prep.py compares it with sbr_host_schedule. */
+sbr_status sbr_fit_plan_read_schedule(const sbr_fit_plan* p, uint64_t* starts, uint32_t* lens, uint32_t* order, size_t cap, size_t* nsub,
+                                      size_t* norder);
 void sbr_fit_plan_free(sbr_fit_plan* p);
 /* stats of the most recent sbr_model_fit on this model */
 sbr_status sbr_model_last_fit_stats(const sbr_model* m, sbr_fit_stats* out);

@@ -32,7 +32,7 @@ SBR_ERR_CUDA, SBR_ERR_NCCL, SBR_ERR_UNSUPPORTED = 4, 5, 6
 EXPORTS = [
     "sbr_last_error_string", "sbr_device_count", "sbr_set_device",
     "sbr_compressed_from_triplets", "sbr_compressed_from_triplets_device", "sbr_compressed_from_csr", "sbr_compressed_borrow_csr", "sbr_compressed_num_users", "sbr_compressed_num_items",
-    "sbr_compressed_len", "sbr_compressed_borrow", "sbr_compressed_user_chunks", "sbr_compressed_upload", "sbr_host_schedule", "sbr_user_based_split", "sbr_train_test_split",
+    "sbr_compressed_len", "sbr_compressed_borrow", "sbr_compressed_user_chunks", "sbr_compressed_upload", "sbr_host_schedule", "sbr_host_master_schedule", "sbr_fit_plan_read_schedule", "sbr_user_based_split", "sbr_train_test_split",
     "sbr_compressed_free",
     "sbr_lstm_hyperparameters_new", "sbr_ewma_hyperparameters_new", "sbr_hyper_learning_rate", "sbr_hyper_l2_penalty",
     "sbr_hyper_embedding_dim", "sbr_hyper_num_epochs", "sbr_hyper_loss", "sbr_hyper_lstm_variant",
@@ -70,7 +70,7 @@ class FitStats(C.Structure):
         ("steps", C.c_uint64), ("timesteps", C.c_uint64), ("partitions", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
         ("train_kernel_ms", C.c_double), ("total_device_ms", C.c_double), ("host_prepare_ms", C.c_double),
-        ("kernel", C.c_char * 64),
+        ("upload_ms", C.c_double), ("kernel", C.c_char * 64),
     ]
 
     def as_dict(self):
@@ -129,6 +129,9 @@ def lib():
     L.sbr_train_test_split.argtypes = [C.c_size_t, C.POINTER(C.c_uint32), C.c_float, u64p, C.POINTER(C.c_size_t)]
     L.sbr_host_schedule.argtypes = [vp, C.c_size_t, C.POINTER(C.c_uint32), u64p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_size_t,
                                     C.POINTER(C.c_size_t)]
+    L.sbr_host_master_schedule.argtypes = [C.POINTER(C.c_uint32), C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32), u64p]
+    L.sbr_fit_plan_read_schedule.argtypes = [vp, u64p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t),
+                                             C.POINTER(C.c_size_t)]
     L.sbr_compressed_free.argtypes = [vp]
     L.sbr_lstm_hyperparameters_new.restype = vp
     L.sbr_lstm_hyperparameters_new.argtypes = [C.c_size_t, C.c_size_t]
@@ -404,6 +407,14 @@ class CompressedInteractions:
         return starts, lens, order, tuple(int(x) for x in st)
 
 
+def host_master_schedule(rng_state, nsub, partitions, threads):
+    """sequence_model.rs:84,97 as fit() does it (sbr_host_master_schedule; host only): (shuffled indices, partition keys, rng state after)."""
+    st = (C.c_uint32 * 4)(*[int(x) for x in rng_state])
+    order = np.zeros(nsub, dtype=np.uint32); keys = np.zeros(max(partitions, 1), dtype=np.uint64)
+    _check(lib().sbr_host_master_schedule(st, nsub, partitions, threads, order.ctypes.data_as(C.POINTER(C.c_uint32)), _p(keys, u64p)))
+    return order, keys[:partitions], tuple(int(x) for x in st)
+
+
 def user_based_split(user_ids, rng_state, test_fraction):
     """data.rs:69-88: boolean mask is_train per interaction (no user in both sets) and the rng state afterwards."""
     u = _u64(user_ids)
@@ -661,6 +672,15 @@ class FitPlan:
         loss = C.c_float()
         _check(lib().sbr_fit_plan_run(self._p, C.byref(loss)))
         return loss.value
+
+    def read_schedule(self):
+        """(starts, lens, order) as staged in HBM: the device chunker's sub-sequences and the partition-major shuffled order."""
+        n, no = C.c_size_t(), C.c_size_t()
+        _check(lib().sbr_fit_plan_read_schedule(self._p, None, None, None, 0, C.byref(n), C.byref(no)))
+        starts = np.zeros(n.value, dtype=np.uint64); lens = np.zeros(n.value, dtype=np.uint32); order = np.zeros(max(n.value, no.value), dtype=np.uint32)
+        _check(lib().sbr_fit_plan_read_schedule(self._p, _p(starts, u64p), lens.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                order.ctypes.data_as(C.POINTER(C.c_uint32)), n.value, C.byref(n), C.byref(no)))
+        return starts, lens, order[:no.value]
 
     def stats(self):
         s = FitStats()

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <future>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -114,64 +115,6 @@ double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// pinned double-buffer used to narrow usize ids to u32 on the way to HBM
-struct Staging {
-    static constexpr size_t kElems = 8u << 20;  // 32 MiB per buffer
-    uint32_t* buf[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2];
-    bool ready = false;
-    std::mutex mu;
-    sbr_status init() {
-        if (ready) return SBR_OK;
-        for (int i = 0; i < 2; ++i) {
-            CU(cudaHostAlloc(&buf[i], kElems * sizeof(uint32_t), cudaHostAllocDefault));
-            CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-        }
-        ready = true;
-        return SBR_OK;
-    }
-};
-Staging g_staging;
-
-// narrow + upload n ids (optionally validating < bound); dst is device memory
-sbr_status upload_ids_u32(const uint64_t* src, size_t n, uint32_t* dst, cudaStream_t st, uint64_t bound, size_t* h2d_bytes) {
-    std::lock_guard<std::mutex> lk(g_staging.mu);
-    sbr_status s = g_staging.init();
-    if (s) return s;
-    size_t done = 0; int b = 0; bool used[2] = {false, false};
-    while (done < n) {
-        const size_t cnt = std::min(Staging::kElems, n - done);
-        if (used[b]) CU(cudaEventSynchronize(g_staging.ev[b]));
-        uint32_t* out = g_staging.buf[b];
-        std::atomic<uint64_t> bad{0};
-        auto narrow = [&](size_t lo, size_t hi) {
-            uint64_t bd = 0;
-            for (size_t i = lo; i < hi; ++i) { const uint64_t v = src[done + i]; bd |= (uint64_t)(v >= bound); out[i] = (uint32_t)v; }
-            if (bd) bad.store(1);
-        };
-        const size_t nth = cnt >= (1u << 20) ? std::min<size_t>(12, std::max(1u, std::thread::hardware_concurrency())) : 1;
-        if (nth <= 1) narrow(0, cnt);
-        else {
-            std::vector<std::thread> th;
-            const size_t per = (cnt + nth - 1) / nth;
-            for (size_t k = 0; k < nth; ++k) th.emplace_back(narrow, std::min(cnt, k * per), std::min(cnt, (k + 1) * per));
-            for (auto& t : th) t.join();
-        }
-        if (bad.load()) return fail(SBR_ERR_INVALID_ARGUMENT, "item id out of range");
-        CU(cudaMemcpyAsync(dst + done, out, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        CU(cudaEventRecord(g_staging.ev[b], st));
-        used[b] = true; b ^= 1; done += cnt;
-    }
-    for (int i = 0; i < 2; ++i) if (used[i]) CU(cudaEventSynchronize(g_staging.ev[i]));
-    if (h2d_bytes) *h2d_bytes += n * sizeof(uint32_t);
-    return SBR_OK;
-}
-
-}  // namespace
-
-// ============================================================================================================
-// handles
-// ============================================================================================================
 // Transient device buffers of a fit() (id stream mirror, schedule arrays) are recycled: cudaMalloc / cudaFree of a
 // 128 MB buffer cost milliseconds each and cudaFree synchronises the device, which shows up directly in the
 // end-to-end (host CSR in, loss out) rate.  Freed blocks are kept on a bounded free list and handed out again to
@@ -218,6 +161,95 @@ struct DevPool {
 DevPool g_pool;
 template <typename T> cudaError_t pool_alloc(T** out, size_t bytes) { void* p = nullptr; cudaError_t e = g_pool.alloc(&p, bytes); *out = static_cast<T*>(p); return e; }
 
+// pinned double-buffer used to narrow usize ids to u32 on the way to HBM
+struct Staging {
+    static constexpr size_t kElems = 8u << 20;  // 32 MiB per buffer
+    uint32_t* buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    bool ready = false;
+    std::mutex mu;
+    sbr_status init() {
+        if (ready) return SBR_OK;
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaHostAlloc(&buf[i], kElems * sizeof(uint32_t), cudaHostAllocDefault));
+            CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        ready = true;
+        return SBR_OK;
+    }
+};
+Staging g_staging;
+
+// narrow + upload n ids (validating < bound); dst is device memory.
+// Pageable source: up to 12 host threads narrow usize -> u32 into a pinned double buffer while the previous piece is on
+// the wire (half the PCIe bytes).  Page-locked source (cudaHostAlloc / cudaHostRegister'ed by the caller): the raw
+// 64-bit words are DMA'ed straight from the caller's buffer, piece by piece, and narrowed by a kernel behind each
+// piece -- no host thread touches the stream.
+sbr_status upload_ids_pinned(const uint64_t* src, size_t n, uint32_t* dst, cudaStream_t st, uint64_t bound, size_t* h2d_bytes) {
+    constexpr size_t kPiece = 4u << 20;   // 32 MiB of raw words per piece; copy and narrow kernel alternate on the stream
+    uint64_t* raw = nullptr; int* d_bad = nullptr;
+    CU(pool_alloc(&raw, std::min(n, kPiece) * sizeof(uint64_t)));
+    if (pool_alloc(&d_bad, 256) != cudaSuccess) { g_pool.release(raw); return cuda_fail(cudaGetLastError(), "cudaMalloc"); }
+    auto done_ = [&](sbr_status r) { g_pool.release(raw); g_pool.release(d_bad); return r; };
+#define CUX(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return done_(cuda_fail(e__, #expr)); } while (0)
+    CUX(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    for (size_t done = 0; done < n; done += kPiece) {
+        const size_t cnt = std::min(kPiece, n - done);
+        CUX(cudaMemcpyAsync(raw, src + done, cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        CUX(launch_narrow_ids(raw, cnt, bound, dst + done, d_bad, st));
+    }
+    int bad = 0;
+    CUX(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUX(cudaStreamSynchronize(st));
+#undef CUX
+    if (h2d_bytes) *h2d_bytes += n * sizeof(uint64_t);
+    if (bad) return done_(fail(SBR_ERR_INVALID_ARGUMENT, "item id out of range"));
+    return done_(SBR_OK);
+}
+
+sbr_status upload_ids_u32(const uint64_t* src, size_t n, uint32_t* dst, cudaStream_t st, uint64_t bound, size_t* h2d_bytes) {
+    if (n >= (1u << 16)) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost) return upload_ids_pinned(src, n, dst, st, bound, h2d_bytes);
+        cudaGetLastError();
+    }
+    std::lock_guard<std::mutex> lk(g_staging.mu);
+    sbr_status s = g_staging.init();
+    if (s) return s;
+    size_t done = 0; int b = 0; bool used[2] = {false, false};
+    while (done < n) {
+        const size_t cnt = std::min(Staging::kElems, n - done);
+        if (used[b]) CU(cudaEventSynchronize(g_staging.ev[b]));
+        uint32_t* out = g_staging.buf[b];
+        std::atomic<uint64_t> bad{0};
+        auto narrow = [&](size_t lo, size_t hi) {
+            uint64_t bd = 0;
+            for (size_t i = lo; i < hi; ++i) { const uint64_t v = src[done + i]; bd |= (uint64_t)(v >= bound); out[i] = (uint32_t)v; }
+            if (bd) bad.store(1);
+        };
+        const size_t nth = cnt >= (1u << 20) ? std::min<size_t>(12, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        if (nth <= 1) narrow(0, cnt);
+        else {
+            std::vector<std::thread> th;
+            const size_t per = (cnt + nth - 1) / nth;
+            for (size_t k = 0; k < nth; ++k) th.emplace_back(narrow, std::min(cnt, k * per), std::min(cnt, (k + 1) * per));
+            for (auto& t : th) t.join();
+        }
+        if (bad.load()) return fail(SBR_ERR_INVALID_ARGUMENT, "item id out of range");
+        CU(cudaMemcpyAsync(dst + done, out, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(g_staging.ev[b], st));
+        used[b] = true; b ^= 1; done += cnt;
+    }
+    for (int i = 0; i < 2; ++i) if (used[i]) CU(cudaEventSynchronize(g_staging.ev[i]));
+    if (h2d_bytes) *h2d_bytes += n * sizeof(uint32_t);
+    return SBR_OK;
+}
+
+}  // namespace
+
+// ============================================================================================================
+// handles
+// ============================================================================================================
 struct sbr_compressed {
     size_t num_users = 0, num_items = 0;
     std::vector<uint64_t> user_ptr, item_ids, timestamps;   // owned storage (empty when borrowed)
@@ -262,6 +294,7 @@ struct sbr_model {
     float* own_dense = nullptr;   // this process's dense buffer (dev.dense points at rank 0's after attach)
     bool attached = true;         // false between build() and sbr_model_ipc_attach() when shard_world > 1
     float* scratch_cache = nullptr; size_t scratch_cap = 0; bool scratch_busy = false;  // grow-only activation scratch
+    uint8_t* h_stage = nullptr; size_t h_stage_cap = 0;   // grow-only pinned staging area of fit(): shuffled order | partition rngs | keys
     ~sbr_model() {
         for (int i = 0; i < 8; ++i) {
             if (own[i]) { if (dev.Es[i]) cudaFree(dev.Es[i]); }
@@ -270,6 +303,7 @@ struct sbr_model {
         if (dev.dense && dev.dense != own_dense) cudaIpcCloseMemHandle(dev.dense);
         if (own_dense) cudaFree(own_dense);
         if (scratch_cache) cudaFree(scratch_cache);
+        if (h_stage) cudaFreeHost(h_stage);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -278,15 +312,15 @@ struct sbr_fit_plan {
     sbr_model* model = nullptr;
     PlanDev dev{};
     uint64_t* d_seq_start = nullptr; uint32_t* d_seq_len = nullptr;
+    void* tmp[2] = {nullptr, nullptr};   // chunker scratch, alive until the plan's staging work has run
     size_t nsub = 0, P = 0, n = 0;
-    uint64_t steps_per_run = 0, timesteps_per_epoch = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     sbr_fit_stats stats{};
     bool scratch_borrowed = false;
     SyncBuffers* sync = nullptr;
     ~sbr_fit_plan() {
         if (sync) sync_buffers_free(sync);
-        g_pool.release(d_seq_start); g_pool.release(d_seq_len);
+        g_pool.release(d_seq_start); g_pool.release(d_seq_len); g_pool.release(tmp[0]); g_pool.release(tmp[1]);
         g_pool.release(dev.order); g_pool.release(dev.rng); g_pool.release(dev.keys);
         g_pool.release(dev.step_ctr); g_pool.release(dev.loss_acc); g_pool.release(dev.examples);
         if (dev.scratch && !scratch_borrowed) cudaFree(dev.scratch);
@@ -297,30 +331,257 @@ struct sbr_fit_plan {
 
 namespace {
 
-sbr_status ensure_uploaded(const sbr_compressed* c, cudaStream_t st) {
+// the CSR's HBM mirror, created lazily: user_ptr first (the device chunker needs nothing else), then the id stream
+sbr_status ensure_user_ptr(const sbr_compressed* c, cudaStream_t st, size_t* bytes) {
     std::lock_guard<std::mutex> lk(c->mu);
-    c->upload_bytes = 0;
+    if (c->d_user_ptr) return SBR_OK;
+    sbr_status s = require_device();
+    if (s) return s;
+    uint64_t* dp = nullptr;
+    CU(pool_alloc(&dp, (c->num_users + 1) * sizeof(uint64_t)));
+    cudaError_t e = cudaMemcpyAsync(dp, c->up_, (c->num_users + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { g_pool.release(dp); return cuda_fail(e, "upload user_ptr"); }
+    c->d_user_ptr = dp;
+    if (bytes) *bytes += (c->num_users + 1) * sizeof(uint64_t);
+    return SBR_OK;
+}
+sbr_status ensure_ids(const sbr_compressed* c, cudaStream_t st, size_t* bytes) {
+    std::lock_guard<std::mutex> lk(c->mu);
     if (c->d_item_ids || c->nnz_ == 0) return SBR_OK;
     sbr_status s = require_device();
     if (s) return s;
-    uint32_t* d = nullptr; uint64_t* dp = nullptr;
+    uint32_t* d = nullptr;
     CU(pool_alloc(&d, std::max<size_t>(c->nnz_, 1) * sizeof(uint32_t)));
-    size_t bytes = 0;
-    s = upload_ids_u32(c->ii_, c->nnz_, d, st, c->num_items, &bytes);
+    s = upload_ids_u32(c->ii_, c->nnz_, d, st, c->num_items, bytes);
     if (s) { g_pool.release(d); return s; }
-    if (pool_alloc(&dp, (c->num_users + 1) * sizeof(uint64_t)) != cudaSuccess) { g_pool.release(d); return cuda_fail(cudaGetLastError(), "cudaMalloc user_ptr"); }
-    cudaError_t e = cudaMemcpyAsync(dp, c->up_, (c->num_users + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { g_pool.release(d); g_pool.release(dp); return cuda_fail(e, "upload user_ptr"); }
-    bytes += (c->num_users + 1) * sizeof(uint64_t);
-    c->d_item_ids = d; c->d_user_ptr = dp; c->upload_bytes = bytes;
+    c->d_item_ids = d;
     return SBR_OK;
 }
+sbr_status ensure_uploaded(const sbr_compressed* c, cudaStream_t st) {
+    size_t bytes = 0;
+    sbr_status s = ensure_user_ptr(c, st, &bytes);
+    if (s == SBR_OK) s = ensure_ids(c, st, &bytes);
+    if (s == SBR_OK && cudaStreamSynchronize(st) != cudaSuccess) s = cuda_fail(cudaGetLastError(), "upload");
+    c->upload_bytes = bytes;
+    return s;
+}
 
-// sequence_model.rs:76-84 on the host: chunk every user (data.rs:406-432: the FIRST chunk is the short one -- len % T
-// items, if that is not 0 -- every later chunk has exactly T items: one division per user), keep len > 2 (:81), then
-// parameters.rng().shuffle(&mut subsequences) (:84): Fisher-Yates from the top.  The swap partners depend on the rng
-// stream only, so they are drawn 16 iterations ahead (same stream, same order) and their cache lines requested early.
+// kept chunks of one user (data.rs:406-432 + the len > 2 filter of sequence_model.rs:81)
+inline size_t user_kept_chunks(uint64_t len, uint64_t T) {
+    if (len == 0) return 0;
+    const uint64_t first = ((len | T) >> 32) == 0 ? (uint64_t)((uint32_t)len % (uint32_t)T) : len % T;
+    return (T > 2 ? (len - first) / T : 0) + (first > 2 ? 1 : 0);
+}
+// number of sub-sequences fit() trains on -- all the host needs to know about them: the chunks themselves are built on
+// the device (data_prep.cu device_schedule) while the host runs the master shuffle over their indices
+size_t host_count_subsequences(const sbr_compressed* c, size_t T) {
+    const size_t U = c->num_users;
+    const size_t nth = U >= (1u << 18) ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    std::vector<size_t> part(nth, 0);
+    auto work = [&](size_t k) {
+        const size_t lo = U * k / nth, hi = U * (k + 1) / nth;
+        size_t n = 0;
+        for (size_t u = lo; u < hi; ++u) n += user_kept_chunks(c->up_[u + 1] - c->up_[u], T);
+        part[k] = n;
+    };
+    if (nth == 1) work(0);
+    else { std::vector<std::thread> th; for (size_t k = 0; k < nth; ++k) th.emplace_back(work, k); for (auto& t : th) t.join(); }
+    size_t n = 0; for (size_t v : part) n += v;
+    return n;
+}
+
+// ---- xorshift128 jump-ahead ----
+// The master rng's stream is what makes the schedule sequential: 2 (nsub - 1) outputs for the shuffle's swap partners
+// (sequence_model.rs:84; ~1.4 x that with gen_range's redraws), then 16 per partition for the thread rngs (:97) -- ~3.5 M
+// dependent steps for the bench stream, 11 ms on one core.  xorshift128 is linear over GF(2): the state after k steps is
+// J^k s.  The stream is cut into segments of 2^14 steps whose start states come from the cached matrix J^(2^14); host
+// threads then produce the segments side by side and the swap loop (inherently sequential, ~3 ns per swap with the
+// partners computed 16 positions ahead) follows behind them.  Same stream, same order, same results as the one-thread
+// loop (tests/test_abi_and_host.py compares both paths).
+struct U128 { uint64_t lo, hi; };   // x = lo[0,32) y = lo[32,64) z = hi[0,32) w = hi[32,64)
+inline U128 xs_pack(const XorShift& r) { return {(uint64_t)r.x | ((uint64_t)r.y << 32), (uint64_t)r.z | ((uint64_t)r.w << 32)}; }
+inline XorShift xs_unpack(const U128& v) { XorShift r; r.x = (uint32_t)v.lo; r.y = (uint32_t)(v.lo >> 32); r.z = (uint32_t)v.hi; r.w = (uint32_t)(v.hi >> 32); return r; }
+struct XsMat {
+    U128 col[128];   // col[i] = image of basis vector e_i
+    U128 apply(U128 v) const {
+        U128 r{0, 0};
+        for (uint64_t m = v.lo; m; m &= m - 1) { const U128& c = col[__builtin_ctzll(m)]; r.lo ^= c.lo; r.hi ^= c.hi; }
+        for (uint64_t m = v.hi; m; m &= m - 1) { const U128& c = col[64 + __builtin_ctzll(m)]; r.lo ^= c.lo; r.hi ^= c.hi; }
+        return r;
+    }
+};
+constexpr int kSegLog2 = 14;
+constexpr size_t kSegSteps = (size_t)1 << kSegLog2;
+const XsMat& xs_segment_jump() {
+    static const XsMat J = [] {
+        XsMat m;
+        for (int i = 0; i < 128; ++i) {
+            U128 e{0, 0};
+            if (i < 64) e.lo = 1ull << i; else e.hi = 1ull << (i - 64);
+            XorShift r = xs_unpack(e);
+            xs_next_u32(r);
+            m.col[i] = xs_pack(r);
+        }
+        for (int k = 0; k < kSegLog2; ++k) {   // square: J <- J . J
+            XsMat n;
+            for (int i = 0; i < 128; ++i) n.col[i] = m.apply(m.col[i]);
+            m = n;
+        }
+        return m;
+    }();
+    return J;
+}
+
+// One-thread reference of the master rng's work in fit(): Fisher-Yates from the top over the indices 0..nsub
+// (parameters.rng().shuffle(&mut subsequences), sequence_model.rs:84), then XorShiftRng::from_seed(parameters.rng().gen())
+// per partition (:97; gen::<[u8; 16]>() takes the low byte of 16 successive outputs).
+void master_shuffle_serial(XorShift& rng, uint32_t* order, size_t nsub) {
+    for (size_t i = 0; i < nsub; ++i) order[i] = (uint32_t)i;
+    constexpr size_t K = 16;
+    size_t js[K];
+    size_t i = nsub, drawn = nsub;
+    auto draw = [&]() {
+        drawn -= 1;
+        const size_t j = (size_t)xs_gen_below(rng, (uint64_t)drawn + 1);
+        js[drawn % K] = j;
+        __builtin_prefetch(order + j, 1);
+    };
+    for (size_t k = 0; k < K && drawn >= 2; ++k) draw();
+    while (i >= 2) {
+        i -= 1;
+        const size_t j = js[i % K];
+        if (drawn >= 2) draw();
+        std::swap(order[i], order[j]);
+    }
+}
+void partition_seeds_serial(XorShift& rng, size_t P, XorShift* rngs, uint64_t* keys) {
+    for (size_t p = 0; p < P; ++p) {
+        uint8_t seed[16];
+        for (int i = 0; i < 16; ++i) seed[i] = (uint8_t)xs_next_u32(rng);
+        xs_from_seed(rngs[p], seed);
+        uint64_t k = 0; for (int i = 0; i < 8; ++i) k |= (uint64_t)seed[i] << (8 * i);
+        keys[p] = k;
+    }
+}
+
+// the same two steps with the rng's output stream produced by `nth` host threads (jump-ahead); P == 0: shuffle only.
+// gen_range redraws while the low product word exceeds its zone (p up to 1/2 per draw), so a swap partner does not sit
+// at a fixed stream position.  Three stages, pipelined: nth - 1 producers fill the raw output stream segment by segment;
+// one thread turns it into the partner list (widening multiply + zone test, in stream order); the caller swaps.
+void master_schedule(XorShift& rng, uint32_t* order, size_t nsub, size_t P, XorShift* rngs, uint64_t* keys, size_t nth) {
+    const size_t ndraw = nsub >= 2 ? nsub - 1 : 0;               // positions nsub - 1 .. 1 each pick a partner
+    if (nth <= 1 || 2 * ndraw + 16 * P < 16 * kSegSteps) {
+        master_shuffle_serial(rng, order, nsub);
+        if (P) partition_seeds_serial(rng, P, rngs, keys);
+        return;
+    }
+    // capacity: every draw accepts with p >= 1/2, so 2 x (2 ndraw) outputs is already twice the expected need
+    const size_t nseg = (4 * ndraw + 16 * P) / kSegSteps + 2;
+    const XorShift rng0 = rng;
+    const XsMat& J = xs_segment_jump();
+    std::vector<U128> start(nseg);
+    start[0] = xs_pack(rng);
+    for (size_t sg = 1; sg < nseg; ++sg) start[sg] = J.apply(start[sg - 1]);
+    // scratch of the calling thread, grow-only: fresh pages cost more than the arithmetic
+    static thread_local std::vector<uint32_t> raw_buf, js_buf;
+    if (raw_buf.size() < nseg * kSegSteps) raw_buf.resize(nseg * kSegSteps);
+    if (js_buf.size() < ndraw) js_buf.resize(ndraw);
+    uint32_t* raw = raw_buf.data();
+    uint32_t* js = js_buf.data();
+    std::unique_ptr<std::atomic<int>[]> ready(new std::atomic<int>[nseg]);
+    for (size_t sg = 0; sg < nseg; ++sg) ready[sg].store(0, std::memory_order_relaxed);
+    std::atomic<size_t> next_seg{0};
+    std::atomic<int> stop{0};
+    auto produce = [&]() {
+        for (;;) {
+            if (stop.load(std::memory_order_relaxed)) return;
+            const size_t sg = next_seg.fetch_add(1);
+            if (sg >= nseg) return;
+            XorShift r = xs_unpack(start[sg]);
+            uint32_t* out = raw + sg * kSegSteps;
+            for (size_t g = 0; g < kSegSteps; ++g) out[g] = xs_next_u32(r);
+            ready[sg].store(1, std::memory_order_release);
+        }
+    };
+    // stage 2, one thread: gen_range over the produced stream, branch-free (a redraw is taken with p up to 1/2 -- as a branch
+    // it mispredicts every third time): the candidate partner is always written, the cursor moves only on acceptance
+    std::atomic<size_t> jdone{0};
+    std::atomic<int> overflow{0};
+    size_t pos_end = 0;
+    auto compact = [&]() {
+        size_t pos = 0, avail = 0, seg_ok = 0, d = 0;
+        uint64_t range = nsub;                       // position i = nsub - 1 - d draws from [0, i] : range i + 1
+        while (d < ndraw) {
+            if (pos + 2 > avail) {
+                if (seg_ok >= nseg) { overflow.store(1); jdone.store(ndraw, std::memory_order_release); return; }
+                while (!ready[seg_ok].load(std::memory_order_acquire)) std::this_thread::yield();
+                ++seg_ok;
+                avail = seg_ok * kSegSteps;
+                jdone.store(d, std::memory_order_release);
+            }
+            const size_t stop_at = avail;
+            while (pos + 2 <= stop_at && d < ndraw) {
+                const uint64_t v = (uint64_t)raw[pos] | ((uint64_t)raw[pos + 1] << 32);
+                pos += 2;
+                const uint64_t zone = (range << clz64(range)) - 1;
+                uint64_t lo;
+                const uint64_t hi = mulhi64(v, range, &lo);
+                js[d] = (uint32_t)hi;
+                const uint64_t acc = lo <= zone ? 1 : 0;
+                d += acc; range -= acc;
+            }
+        }
+        pos_end = pos;
+        jdone.store(ndraw, std::memory_order_release);
+    };
+    std::vector<std::thread> th;
+    for (size_t k = 0; k + 1 < nth; ++k) th.emplace_back(produce);
+    th.emplace_back(compact);
+    struct Stopper { std::atomic<int>& s; std::vector<std::thread>& t; ~Stopper() { s.store(1); for (auto& x : t) x.join(); } } stopper{stop, th};
+    // stage 3, this thread: the swaps, partners known ahead
+    for (size_t i = 0; i < nsub; ++i) order[i] = (uint32_t)i;
+    {
+        constexpr size_t K = 16;
+        size_t have = 0;
+        for (size_t d = 0; d < ndraw; ++d) {
+            const size_t pf = std::min(d + K, ndraw - 1);
+            while (pf >= have) { have = jdone.load(std::memory_order_acquire); if (pf >= have) std::this_thread::yield(); }
+            __builtin_prefetch(order + js[pf], 1);
+            std::swap(order[nsub - 1 - d], order[js[d]]);
+        }
+    }
+    th.back().join(); th.pop_back();   // the compactor (pos_end is final)
+    size_t pos = pos_end;
+    bool bad = overflow.load() != 0;
+    if (!bad) {
+        const size_t need_seg = (pos + 16 * P + kSegSteps - 1) / kSegSteps;
+        if (need_seg > nseg) bad = true;
+        else for (size_t sg = 0; sg < need_seg; ++sg) while (!ready[sg].load(std::memory_order_acquire)) std::this_thread::yield();
+    }
+    if (bad) {   // (the stream ran past twice its expected length: never observed) redo as the plain loop
+        rng = rng0;
+        master_shuffle_serial(rng, order, nsub);
+        if (P) partition_seeds_serial(rng, P, rngs, keys);
+        return;
+    }
+    for (size_t p = 0; p < P; ++p) {
+        uint8_t seed[16];
+        for (int i = 0; i < 16; ++i) seed[i] = (uint8_t)raw[pos + 16 * p + i];
+        xs_from_seed(rngs[p], seed);
+        uint64_t k = 0; for (int i = 0; i < 8; ++i) k |= (uint64_t)seed[i] << (8 * i);
+        keys[p] = k;
+    }
+    pos += 16 * P;
+    XorShift r = xs_unpack(start[pos / kSegSteps]);   // the rng after everything consumed
+    for (size_t g = 0; g < pos % kSegSteps; ++g) xs_next_u32(r);
+    rng = r;
+}
+void master_shuffle(XorShift& rng, uint32_t* order, size_t nsub) { master_schedule(rng, order, nsub, 0, nullptr, nullptr, 1); }
+
+// sequence_model.rs:76-84 entirely on the host (the sbr_host_schedule hook: CPU-only CI pins it on the oracle; fit() builds
+// the chunks on the device instead and is tested against this function): chunk every user (data.rs:406-432: the FIRST chunk
+// is the short one -- len % T items, if that is not 0 -- every later chunk has exactly T items), keep len > 2 (:81), then
+// the master shuffle (:84).
 sbr_status host_schedule(const sbr_compressed* c, size_t T, XorShift& rng, std::vector<uint64_t>& starts, std::vector<uint32_t>& lens,
                          std::vector<uint32_t>& order) {
     if (T == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "max_sequence_length must be positive");
@@ -338,23 +599,7 @@ sbr_status host_schedule(const sbr_compressed* c, size_t T, XorShift& rng, std::
     if (nsub == 0) return fail(SBR_ERR_NO_INTERACTIONS, "No interactions were supplied.");  // :86-88
     if (nsub > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "too many sub-sequences");
     order.resize(nsub);
-    for (size_t i = 0; i < nsub; ++i) order[i] = (uint32_t)i;
-    constexpr size_t K = 16;
-    size_t js[K];
-    size_t i = nsub, drawn = nsub;
-    auto draw = [&]() {
-        drawn -= 1;
-        const size_t j = (size_t)xs_gen_below(rng, (uint64_t)drawn + 1);
-        js[drawn % K] = j;
-        __builtin_prefetch(order.data() + j, 1);
-    };
-    for (size_t k = 0; k < K && drawn >= 2; ++k) draw();
-    while (i >= 2) {
-        i -= 1;
-        const size_t j = js[i % K];
-        if (drawn >= 2) draw();
-        std::swap(order[i], order[j]);
-    }
+    master_shuffle(rng, order.data(), nsub);
     return SBR_OK;
 }
 
@@ -1040,7 +1285,22 @@ sbr_status sbr_host_schedule(const sbr_compressed* c, size_t max_sequence_length
     return SBR_OK;
 }
 
+sbr_status sbr_host_master_schedule(uint32_t rng_state[4], size_t nsub, size_t partitions, size_t threads, uint32_t* order, uint64_t* keys) {
+    if (!rng_state || !order || (partitions && !keys)) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    if ((rng_state[0] | rng_state[1] | rng_state[2] | rng_state[3]) == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "xorshift state must not be all zero");
+    if (nsub > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "too many sub-sequences");
+    XorShift rng; rng.x = rng_state[0]; rng.y = rng_state[1]; rng.z = rng_state[2]; rng.w = rng_state[3];
+    std::vector<XorShift> rngs(partitions);
+    master_schedule(rng, order, nsub, partitions, rngs.data(), keys, threads);
+    rng_state[0] = rng.x; rng_state[1] = rng.y; rng_state[2] = rng.z; rng_state[3] = rng.w;
+    return SBR_OK;
+}
+
 // --------------------------------------------------------------------------------------------------- fit ----
+// Order of business (everything the device can do is on the model's stream, the host never waits before the end):
+//   main thread : user_ptr -> HBM, device chunker (data_prep.cu) enqueued          | count sub-sequences (threads), master shuffle
+//   upload thread:                                  id stream -> HBM (narrowed)     |   of their indices into a pinned buffer,
+//   then: order / rngs / keys -> HBM from the pinned buffer; the plan is ready when the stream is.                partition rngs
 sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_plan** out) {
     if (!m || !c || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     sbr_status s = require_device();
@@ -1048,66 +1308,75 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     if (c->num_items > m->dev.N) return fail(SBR_ERR_INVALID_ARGUMENT, "interactions.num_items exceeds the model's num_items");
     const double t0 = now_ms();
     const size_t T = (size_t)m->dev.T;
-    // the id stream goes to HBM (narrowed to u32, pinned double buffer) while the host builds the schedule
-    cudaStream_t st = m->stream;
-    cudaEvent_t ev_begin = nullptr;
-    CU(cudaEventCreate(&ev_begin));
-    CU(cudaEventRecord(ev_begin, st));
-    std::string up_err;
-    std::future<sbr_status> up = std::async(std::launch::async, [&]() {
-        cudaSetDevice(g_device);
-        sbr_status r = ensure_uploaded(c, st);
-        if (r) up_err = g_err;
-        return r;
-    });
-    struct Joiner { std::future<sbr_status>& f; cudaEvent_t& e; bool taken = false;
-                    ~Joiner() { if (f.valid()) f.wait(); if (e && !taken) cudaEventDestroy(e); } } joiner{up, ev_begin};
-    // sequence_model.rs:76-84: sub-sequences of every user, filtered, shuffled with the master rng
-    std::vector<uint64_t> starts; std::vector<uint32_t> lens; std::vector<uint32_t> order;
-    uint64_t timesteps = 0;
+    if (T == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "max_sequence_length must be positive");
     std::lock_guard<std::mutex> lk(m->mu);
-    s = host_schedule(c, T, m->rng, starts, lens, order);
-    if (s) return s;
-    const size_t nsub = starts.size();
+    cudaStream_t st = m->stream;
+    // sequence_model.rs:76-81: how many sub-sequences survive the len > 2 filter (the chunks themselves: device, below)
+    const size_t nsub = host_count_subsequences(c, T);
+    if (nsub == 0) return fail(SBR_ERR_NO_INTERACTIONS, "No interactions were supplied.");  // :86-88
+    if (nsub > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "too many sub-sequences");
     // :90-98 partitions
     size_t P = m->h.num_threads;
     if (P == 0) {
         const size_t autoP = (size_t)train_auto_partitions(m->dev, device_info().sms);
         P = std::min(autoP, std::max<size_t>(1, nsub / 16));
-        // the LSTM tile kernels take whole tiles of 128 partitions (2 tiles per CTA): round down so that real data
+        // the D = 32 tile kernels take whole tiles of 128 partitions (2 tiles per CTA): round down so that real data
         // (nsub / 16 is almost never a multiple of 128) still runs on them
         if (m->dev.D == 32 && !m->dev.exact) { if (P >= 256) P -= P % 256; else if (P >= 128) P = 128; }
     }
     if (P > nsub) return fail(SBR_ERR_INVALID_ARGUMENT, "num_threads exceeds the number of sub-sequences (the reference panics in chunks_mut(0))");
     const size_t n = nsub / P;  // :91, remainder dropped by the zip at :94-96
-    std::vector<XorShift> rngs(P); std::vector<uint64_t> keys(P);
-    for (size_t p = 0; p < P; ++p) {  // :97 XorShiftRng::from_seed(parameters.rng().gen())
-        uint8_t seed[16];
-        for (int i = 0; i < 16; ++i) seed[i] = (uint8_t)xs_next_u32(m->rng);
-        xs_from_seed(rngs[p], seed);
-        uint64_t k = 0; for (int i = 0; i < 8; ++i) k |= (uint64_t)seed[i] << (8 * i);
-        keys[p] = k;
-    }
-    for (size_t i = 0; i < nsub; ++i) timesteps += lens[i] - 1;                       // all sub-sequences ...
-    for (size_t i = P * n; i < nsub; ++i) timesteps -= lens[order[i]] - 1;            // ... minus the remainder the zip at :94-96 drops
-    const double t1 = now_ms();
 
     sbr_fit_plan* pl = new (std::nothrow) sbr_fit_plan();
     if (!pl) return fail(SBR_ERR_INVALID_ARGUMENT, "out of memory");
     pl->model = m; pl->nsub = nsub; pl->P = P; pl->n = n;
-    pl->timesteps_per_epoch = timesteps;
-    pl->stats.host_prepare_ms = t1 - t0;
-    auto bail = [&](sbr_status r) { delete pl; return r; };
+    std::string up_err;
+    std::future<sbr_status> up;
+    struct Joiner { std::future<sbr_status>& f; ~Joiner() { if (f.valid()) f.wait(); } } joiner{up};   // never outlive the upload thread
+    auto bail = [&](sbr_status r) { if (up.valid()) up.wait(); delete pl; return r; };
 #define CUP(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return bail(cuda_fail(e__, #expr)); } while (0)
-    for (cudaEvent_t* e : {&pl->ev1, &pl->evk0, &pl->evk1}) CUP(cudaEventCreate(e));
-    pl->ev0 = ev_begin; joiner.taken = true;
-    s = up.get();
-    if (s) { g_err = up_err; return bail(s); }
-    size_t h2d = c->upload_bytes;
+    for (cudaEvent_t* e : {&pl->ev0, &pl->ev1, &pl->evk0, &pl->evk1}) CUP(cudaEventCreate(e));
+    CUP(cudaEventRecord(pl->ev0, st));
+    size_t h2d = 0;
     PlanDev& d = pl->dev;
-    d.item_ids = c->d_item_ids;
+    // ---- device: user_ptr, then the chunker ----
+    s = ensure_user_ptr(c, st, &h2d);
+    if (s) return bail(s);
     CUP(pool_alloc(&pl->d_seq_start, nsub * sizeof(uint64_t)));
     CUP(pool_alloc(&pl->d_seq_len, nsub * sizeof(uint32_t)));
+    {
+        uint32_t* d_counts = nullptr; void* d_tmp = nullptr; size_t tmp_bytes = 0;
+        CUP(device_schedule(nullptr, c->num_users, T, nullptr, nullptr, &tmp_bytes, nsub, nullptr, nullptr, st));
+        CUP(pool_alloc(&d_counts, (c->num_users + 1) * sizeof(uint32_t)));
+        pl->tmp[0] = d_counts;
+        CUP(pool_alloc(&d_tmp, std::max<size_t>(tmp_bytes, 256)));
+        pl->tmp[1] = d_tmp;
+        CUP(device_schedule(c->d_user_ptr, c->num_users, T, d_counts, d_tmp, &tmp_bytes, nsub, pl->d_seq_start, pl->d_seq_len, st));
+    }
+    // ---- upload thread: the id stream (a no-op when the CSR is already resident) ----
+    const double tu0 = now_ms();
+    double upload_ms = 0.0;
+    size_t id_bytes = 0;
+    up = std::async(std::launch::async, [&]() {
+        cudaSetDevice(g_device);
+        sbr_status r = ensure_ids(c, st, &id_bytes);
+        if (r) up_err = g_err;
+        upload_ms = now_ms() - tu0;
+        return r;
+    });
+    // ---- host: master shuffle of the indices (:84) + per-partition rngs (:97) into the model's pinned staging area ----
+    const size_t stage_bytes = nsub * sizeof(uint32_t) + P * (sizeof(XorShift) + sizeof(uint64_t)) + 64;
+    if (m->h_stage_cap < stage_bytes) {
+        if (m->h_stage) { cudaFreeHost(m->h_stage); m->h_stage = nullptr; m->h_stage_cap = 0; }
+        CUP(cudaHostAlloc(&m->h_stage, stage_bytes + (stage_bytes >> 2), cudaHostAllocDefault));
+        m->h_stage_cap = stage_bytes + (stage_bytes >> 2);
+    }
+    uint32_t* h_order = reinterpret_cast<uint32_t*>(m->h_stage);
+    XorShift* h_rngs = reinterpret_cast<XorShift*>(m->h_stage + ((nsub * sizeof(uint32_t) + 15) & ~(size_t)15));
+    uint64_t* h_keys = reinterpret_cast<uint64_t*>(h_rngs + P);
+    master_schedule(m->rng, h_order, nsub, P, h_rngs, h_keys, std::min<size_t>(4, std::max(1u, std::thread::hardware_concurrency())));
+    pl->stats.host_prepare_ms = now_ms() - t0;
+
     CUP(pool_alloc(&d.order, P * n * sizeof(uint32_t)));
     CUP(pool_alloc(&d.rng, P * sizeof(XorShift)));
     CUP(pool_alloc(&d.keys, P * sizeof(uint64_t)));
@@ -1126,16 +1395,21 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
             d.scratch = m->scratch_cache; pl->scratch_borrowed = true; m->scratch_busy = true;
         } else CUP(cudaMalloc(&d.scratch, need));
     }
-    CUP(cudaMemcpyAsync(pl->d_seq_start, starts.data(), nsub * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    CUP(cudaMemcpyAsync(pl->d_seq_len, lens.data(), nsub * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CUP(cudaMemcpyAsync(d.order, order.data(), P * n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CUP(cudaMemcpyAsync(d.rng, rngs.data(), P * sizeof(XorShift), cudaMemcpyHostToDevice, st));
-    CUP(cudaMemcpyAsync(d.keys, keys.data(), P * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    s = up.get();   // the id copies are enqueued (and done); what follows queues behind them
+    if (s) { g_err = up_err; return bail(s); }
+    h2d += id_bytes;
+    c->upload_bytes = id_bytes;
+    pl->stats.upload_ms = upload_ms;
+    d.item_ids = c->d_item_ids;
+    CUP(cudaMemcpyAsync(d.order, h_order, P * n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CUP(cudaMemcpyAsync(d.rng, h_rngs, P * sizeof(XorShift), cudaMemcpyHostToDevice, st));
+    CUP(cudaMemcpyAsync(d.keys, h_keys, P * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CUP(cudaMemsetAsync(d.step_ctr, 0, P * sizeof(uint64_t), st));
     CUP(cudaMemsetAsync(d.loss_acc, 0, P * sizeof(float), st));
     CUP(cudaMemsetAsync(d.examples, 0, P * sizeof(unsigned long long), st));
-    CUP(cudaStreamSynchronize(st));  // host vectors go out of scope
-    h2d += nsub * 12 + P * n * 4 + P * (sizeof(XorShift) + 8);
+    CUP(cudaStreamSynchronize(st));   // the model's pinned staging area is free again; chunker scratch can go back to the pool
+    g_pool.release(pl->tmp[0]); g_pool.release(pl->tmp[1]); pl->tmp[0] = pl->tmp[1] = nullptr;
+    h2d += P * n * 4 + P * (sizeof(XorShift) + 8);
     d.seq_start = pl->d_seq_start; d.seq_len = pl->d_seq_len;
     d.n = (uint32_t)n; d.P = (uint32_t)P;
     d.neg_range = (uint32_t)c->num_items;  // :74 Uniform::new(0, interactions.num_items())
@@ -1209,6 +1483,21 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
 sbr_status sbr_fit_plan_stats(const sbr_fit_plan* p, sbr_fit_stats* out) {
     if (!p || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     *out = p->stats;
+    return SBR_OK;
+}
+sbr_status sbr_fit_plan_read_schedule(const sbr_fit_plan* p, uint64_t* starts, uint32_t* lens, uint32_t* order, size_t cap, size_t* nsub,
+                                      size_t* norder) {
+    if (!p || !nsub || !norder) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
+    *nsub = p->nsub; *norder = p->P * p->n;
+    if (!starts || !lens || !order || cap < p->nsub) return SBR_OK;
+    sbr_status s = require_device();
+    if (s) return s;
+    std::lock_guard<std::mutex> lk(p->model->mu);
+    cudaStream_t st = p->model->stream;
+    CU(cudaMemcpyAsync(starts, p->d_seq_start, p->nsub * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(lens, p->d_seq_len, p->nsub * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(order, p->dev.order, p->P * p->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return SBR_OK;
 }
 void sbr_fit_plan_free(sbr_fit_plan* p) { if (p) { cudaSetDevice(g_device); delete p; } }

@@ -123,3 +123,87 @@ int device_csr_build(const uint64_t* h_user, const uint64_t* h_item, const uint6
 }
 
 }  // namespace sbr
+
+// ============================================================================================================
+// sequence_model.rs:76-81 on the device: the sub-sequences of every user (data.rs:406-432: the FIRST chunk is the short
+// one -- len % T items, if that is not 0 -- every later chunk has exactly T items), filtered to len > 2 (:81), in user
+// order.  Three launches over the resident user_ptr: kept chunks per user -> exclusive scan -> one thread per kept chunk
+// (the owning user found by binary search in the scanned offsets, so a user with a million interactions costs no more
+// per thread than one with three).  Bit-identical to host_schedule() in api.cu (tests/test_gpu_data_prep.py).
+// ============================================================================================================
+namespace sbr {
+namespace {
+
+__device__ __forceinline__ void user_chunks(uint64_t len, uint64_t T, uint32_t* kept, uint32_t* first_kept, uint64_t* first) {
+    uint64_t f = 0; uint32_t k = 0, fk = 0;
+    if (len > 0) {
+        f = (len >> 32) == 0 && (T >> 32) == 0 ? (uint64_t)((uint32_t)len % (uint32_t)T) : len % T;
+        const uint64_t full = T > 2 ? (len - f) / T : 0;
+        fk = f > 2 ? 1u : 0u;
+        k = (uint32_t)full + fk;
+    }
+    *kept = k; *first_kept = fk; *first = f;
+}
+
+__global__ void sched_count_kernel(const uint64_t* __restrict__ user_ptr, size_t num_users, uint64_t T, uint32_t* __restrict__ counts) {
+    for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < num_users; u += (size_t)gridDim.x * blockDim.x) {
+        uint32_t k, fk; uint64_t f;
+        user_chunks(user_ptr[u + 1] - user_ptr[u], T, &k, &fk, &f);
+        counts[u] = k;
+    }
+}
+
+// offsets = exclusive scan of counts, offsets[num_users] = nsub
+__global__ void sched_fill_kernel(const uint64_t* __restrict__ user_ptr, const uint32_t* __restrict__ offsets, size_t num_users, uint64_t T,
+                                  size_t nsub, uint64_t* __restrict__ seq_start, uint32_t* __restrict__ seq_len) {
+    for (size_t s = blockIdx.x * (size_t)blockDim.x + threadIdx.x; s < nsub; s += (size_t)gridDim.x * blockDim.x) {
+        size_t lo = 0, hi = num_users;            // last user u with offsets[u] <= s  (users without kept chunks share offsets: take the last)
+        while (hi - lo > 1) { const size_t mid = (lo + hi) >> 1; if (offsets[mid] <= s) lo = mid; else hi = mid; }
+        const uint64_t b = user_ptr[lo], len = user_ptr[lo + 1] - b;
+        uint32_t k, fk; uint64_t f;
+        user_chunks(len, T, &k, &fk, &f);
+        const uint32_t j = (uint32_t)(s - offsets[lo]);   // j-th kept chunk of this user
+        if (fk && j == 0) { seq_start[s] = b; seq_len[s] = (uint32_t)f; }
+        else { seq_start[s] = b + f + (uint64_t)(j - fk) * T; seq_len[s] = (uint32_t)T; }
+    }
+}
+
+// usize ids -> u32 on the device (ids that arrived as raw 64-bit words from pinned host memory)
+__global__ void narrow_ids_kernel(const uint64_t* __restrict__ src, size_t n, uint64_t bound, uint32_t* __restrict__ dst, int* __restrict__ bad) {
+    int b = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t v = src[i];
+        b |= (int)(v >= bound);
+        dst[i] = (uint32_t)v;
+    }
+    if (b) atomicOr(bad, 1);
+}
+
+}  // namespace
+
+// d_counts: [num_users + 1] u32 scratch (becomes the offsets), d_tmp: CUB scratch of *tmp_bytes (query with d_tmp == nullptr)
+cudaError_t device_schedule(const uint64_t* d_user_ptr, size_t num_users, size_t T, uint32_t* d_counts, void* d_tmp, size_t* tmp_bytes, size_t nsub,
+                            uint64_t* d_seq_start, uint32_t* d_seq_len, cudaStream_t st) {
+    if (!d_tmp) return cub::DeviceScan::ExclusiveSum(nullptr, *tmp_bytes, d_counts, d_counts, (int)(num_users + 1), st);
+    const int threads = 256;
+    const int bu = (int)std::min<size_t>((num_users + threads - 1) / threads, 148 * 16);
+    cudaError_t e = cudaMemsetAsync(d_counts + num_users, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    if (num_users) sched_count_kernel<<<std::max(bu, 1), threads, 0, st>>>(d_user_ptr, num_users, (uint64_t)T, d_counts);
+    e = cub::DeviceScan::ExclusiveSum(d_tmp, *tmp_bytes, d_counts, d_counts, (int)(num_users + 1), st);
+    if (e != cudaSuccess) return e;
+    if (nsub) {
+        const int bs = (int)std::min<size_t>((nsub + threads - 1) / threads, 148 * 16);
+        sched_fill_kernel<<<bs, threads, 0, st>>>(d_user_ptr, d_counts, num_users, (uint64_t)T, nsub, d_seq_start, d_seq_len);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_narrow_ids(const uint64_t* d_src, size_t n, uint64_t bound, uint32_t* d_dst, int* d_bad, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    narrow_ids_kernel<<<blocks, 256, 0, st>>>(d_src, n, bound, d_dst, d_bad);
+    return cudaGetLastError();
+}
+
+}  // namespace sbr

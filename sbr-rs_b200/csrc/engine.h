@@ -93,6 +93,11 @@ int device_csr_build(const uint64_t* h_user, const uint64_t* h_item, const uint6
                      uint64_t* h_user_ptr, uint64_t* h_item_out, uint64_t* h_ts_out, uint32_t* d_item_u32, uint64_t* d_user_ptr,
                      cudaStream_t st, std::string* err);
 
+// sequence_model.rs:76-81 on the device (data_prep.cu): chunks of every user, len > 2 filter, in user order
+cudaError_t device_schedule(const uint64_t* d_user_ptr, size_t num_users, size_t T, uint32_t* d_counts, void* d_tmp, size_t* tmp_bytes, size_t nsub,
+                            uint64_t* d_seq_start, uint32_t* d_seq_len, cudaStream_t st);
+cudaError_t launch_narrow_ids(const uint64_t* d_src, size_t n, uint64_t bound, uint32_t* d_dst, int* d_bad, cudaStream_t st);
+
 cudaError_t launch_gather_rows(const ModelDev& m, const uint32_t* ids_dev, size_t n, float* out_dev, cudaStream_t st);
 cudaError_t launch_user_representations(const ModelDev& m, const uint64_t* ptr_dev, const uint32_t* ids_dev, size_t num_users,
                                         float* out_dev, cudaStream_t st);

@@ -202,6 +202,31 @@ def test_host_schedule_equals_oracle(pkg, oracle, T, min_len, max_len):
     assert int(slens.min()) > 2 and int(slens.max()) <= T
 
 
+@pytest.mark.parametrize("nsub,partitions,threads", [(1, 1, 4), (2, 2, 4), (1000, 7, 4), (140001, 128, 2), (300000, 0, 4), (600000, 4096, 8)])
+def test_master_schedule_with_jump_ahead_equals_oracle(pkg, oracle, nsub, partitions, threads):
+    """What fit() does with the master rng -- Fisher-Yates over the sub-sequence indices (sequence_model.rs:84), then one
+    [u8; 16] seed per partition (:97) -- with the xorshift128 stream produced by several host threads (jump-ahead through
+    the GF(2) transition matrix, partner list built in stream order with gen_range's redraws) is bit-identical to the
+    oracle's plain loops and to the library's own one-thread path: order, partition keys, rng state afterwards."""
+    import ctypes as C
+    r = oracle.make_rng(bytes(range(3, 19)))
+    state0 = (r.x, r.y, r.z, r.w)
+    order, keys, state1 = pkg.host_master_schedule(state0, nsub, partitions, threads)
+    order1, keys1, state11 = pkg.host_master_schedule(state0, nsub, partitions, 1)
+    assert np.array_equal(order, order1) and np.array_equal(keys, keys1) and state1 == state11
+    oorder = np.arange(nsub, dtype=np.uint32)
+    L = oracle.lib()
+    L.sbo_shuffle_u32(C.byref(r), oorder.ctypes.data_as(oracle.u32p), nsub)
+    assert np.array_equal(order, oorder)
+    okeys = []
+    for _ in range(partitions):
+        seed = bytes(L.sbo_rng_next_u32(C.byref(r)) & 0xFF for _ in range(16))
+        okeys.append(int.from_bytes(seed[:8], "little"))
+    assert np.array_equal(keys, np.array(okeys, dtype=np.uint64))
+    assert state1 == (r.x, r.y, r.z, r.w)
+    assert np.array_equal(np.sort(order), np.arange(nsub, dtype=np.uint32))
+
+
 def test_host_schedule_empty_is_no_interactions(pkg):
     ptr = np.array([0, 2, 3, 5], dtype=np.uint64)          # every user has <= 2 interactions: nothing survives the filter
     ids = np.array([1, 2, 3, 4, 5], dtype=np.uint64)
