@@ -318,8 +318,11 @@ struct sbr_fit_plan {
     sbr_fit_stats stats{};
     bool scratch_borrowed = false;
     SyncBuffers* sync = nullptr;
+    BatchBuffers* batch = nullptr;
+    bool use_batch = false;   // LSTM on the round-synchronous batched tensor-core engine (lstm_batch.cuh)
     ~sbr_fit_plan() {
         if (sync) sync_buffers_free(sync);
+        if (batch) batch_buffers_free(batch);
         g_pool.release(d_seq_start); g_pool.release(d_seq_len); g_pool.release(tmp[0]); g_pool.release(tmp[1]);
         g_pool.release(dev.order); g_pool.release(dev.rng); g_pool.release(dev.keys);
         g_pool.release(dev.step_ctr); g_pool.release(dev.loss_acc); g_pool.release(dev.examples);
@@ -1323,6 +1326,7 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
         // the D = 32 tile kernels take whole tiles of 128 partitions (2 tiles per CTA): round down so that real data
         // (nsub / 16 is almost never a multiple of 128) still runs on them
         if (m->dev.D == 32 && !m->dev.exact) { if (P >= 256) P -= P % 256; else if (P >= 128) P = 128; }
+        if (m->dev.model == MODEL_LSTM && m->dev.D > 32 && !m->dev.exact && P >= 128) P -= P % 128;
     }
     if (P > nsub) return fail(SBR_ERR_INVALID_ARGUMENT, "num_threads exceeds the number of sub-sequences (the reference panics in chunks_mut(0))");
     const size_t n = nsub / P;  // :91, remainder dropped by the zip at :94-96
@@ -1330,6 +1334,13 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     sbr_fit_plan* pl = new (std::nothrow) sbr_fit_plan();
     if (!pl) return fail(SBR_ERR_INVALID_ARGUMENT, "out of memory");
     pl->model = m; pl->nsub = nsub; pl->P = P; pl->n = n;
+    {   // which engine: LSTM under Parallelism::Synchronous (any width), and the wide LSTMs with many partitions, run in rounds
+        const char* why = nullptr;
+        const bool can = m->dev.model == MODEL_LSTM && g_world <= 1 && m->h.shard_world <= 1 && batch_lstm_supported(m->dev, (uint32_t)P, &why);
+        const bool sync_lstm = m->dev.model == MODEL_LSTM && m->h.parallelism == SBR_PARALLELISM_SYNCHRONOUS && P > 1;
+        if (sync_lstm && !can) { delete pl; return fail(SBR_ERR_INVALID_ARGUMENT, std::string("Parallelism::Synchronous LSTM fit: ") + (why ? why : "one process / unsharded table only")); }
+        pl->use_batch = can && (sync_lstm || (m->dev.D > 32 && !m->dev.exact && P >= 128));
+    }
     std::string up_err;
     std::future<sbr_status> up;
     struct Joiner { std::future<sbr_status>& f; ~Joiner() { if (f.valid()) f.wait(); } } joiner{up};   // never outlive the upload thread
@@ -1383,7 +1394,7 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     CUP(pool_alloc(&d.step_ctr, P * sizeof(uint64_t)));
     CUP(pool_alloc(&d.loss_acc, P * sizeof(float)));
     CUP(pool_alloc(&d.examples, P * sizeof(unsigned long long)));
-    d.scratch_stride = train_scratch_floats_per_warp(m->dev);
+    d.scratch_stride = pl->use_batch ? 32 : train_scratch_floats_per_warp(m->dev);
     {
         const size_t need = P * d.scratch_stride * sizeof(float);
         if (!m->scratch_busy) {   // the model keeps one grow-only scratch buffer across fit() calls
@@ -1438,7 +1449,13 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
     uint64_t sync_rounds = 0;
     const bool sync_mode = m->h.parallelism == SBR_PARALLELISM_SYNCHRONOUS && (P > 1 || g_world > 1) && sync_supported(m->dev, &why) &&
                            (int)(m->dev.gmask + 1) == (m->h.shard_world > 1 ? m->h.shard_world : 1);
-    if (pl->dev.epochs > 0 && sync_mode) {
+    if (pl->dev.epochs > 0 && pl->use_batch) {
+        if (!pl->batch) pl->batch = batch_buffers_new();
+        std::string err;
+        const int rc = run_batch_lstm(m->dev, pl->dev, *pl->batch, m->num_updates, device_info().sms, st, &launches, &sync_rounds, &err);
+        if (rc) return fail(SBR_ERR_CUDA, err);
+        std::snprintf(pl->stats.kernel, sizeof(pl->stats.kernel), "bl_fwd/bl_dz/bl_dw_kernel D=%d (batched tcgen05 LSTM engine)", m->dev.D);
+    } else if (pl->dev.epochs > 0 && sync_mode) {
         // Parallelism::Synchronous: round-synchronous schedule with an explicit row exchange (sync_engine.cu)
         const int world = m->h.shard_world > 1 ? m->h.shard_world : 1;
         if (world > 1 && (!g_comm || g_world != world || g_rank != m->h.shard_rank))
@@ -1467,7 +1484,7 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
     CU(cudaStreamSynchronize(st));
     float total = 0.0f; uint64_t tsteps = 0;
     for (size_t p = 0; p < P; ++p) { total += loss[p] / (1.0f + (float)ex[p]); tsteps += ex[p]; }  // :173-175
-    const uint64_t steps = (sync_mode && pl->dev.epochs > 0) ? (uint64_t)P * sync_rounds : (uint64_t)P * pl->n * (uint64_t)pl->dev.epochs;
+    const uint64_t steps = ((sync_mode || pl->use_batch) && pl->dev.epochs > 0) ? (uint64_t)P * sync_rounds : (uint64_t)P * pl->n * (uint64_t)pl->dev.epochs;
     m->num_updates += steps;
     float kms = 0.0f, tms = 0.0f;
     CU(cudaEventElapsedTime(&kms, pl->evk0, pl->evk1));

@@ -88,6 +88,15 @@ namespace sbr {
 int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm, int rank, int world, uint64_t num_updates,
                   cudaStream_t st, int* launches, uint64_t* rounds_out, std::string* err);
 
+// round-synchronous batched LSTM engine on tcgen05 GEMMs (lstm_batch.cuh): Parallelism::Synchronous for LSTM models and the
+// throughput path of embedding_dim 64 / 128 / 256
+struct BatchBuffers;
+BatchBuffers* batch_buffers_new();
+void batch_buffers_free(BatchBuffers* b);
+bool batch_lstm_supported(const ModelDev& m, uint32_t P, const char** why);
+int run_batch_lstm(const ModelDev& m, PlanDev& pl, BatchBuffers& B, uint64_t num_updates, int num_sms, cudaStream_t st, int* launches,
+                   uint64_t* rounds_out, std::string* err);
+
 // Interactions::to_compressed on the device (data_prep.cu): 0 ok, 1 CUDA error, 2 invalid argument
 int device_csr_build(const uint64_t* h_user, const uint64_t* h_item, const uint64_t* h_ts, size_t nnz, size_t num_users, size_t num_items,
                      uint64_t* h_user_ptr, uint64_t* h_item_out, uint64_t* h_ts_out, uint32_t* d_item_u32, uint64_t* d_user_ptr,

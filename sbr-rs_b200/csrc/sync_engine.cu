@@ -21,8 +21,13 @@
 #include <string>
 #include <vector>
 
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
 #include "engine.h"
 #include "nccl_dyn.h"
+#include "tc_tile.cuh"
 
 namespace sbr {
 
@@ -214,6 +219,7 @@ __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, c
     const int lane = threadIdx.x & 31;
     for (size_t j = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += (size_t)gridDim.x * (blockDim.x >> 5)) {
         const uint32_t r = (uint32_t)(keys[j] >> 32);
+        if (r == kInvalid) continue;                                 // unused slot (sorted to the end)
         if (j > 0 && (uint32_t)(keys[j - 1] >> 32) == r) continue;   // not the first entry of its row
         for (size_t e = j; e < n && (uint32_t)(keys[e] >> 32) == r; ++e) {
             const uint32_t src = vals[e];
@@ -276,6 +282,11 @@ void sync_buffers_free(SyncBuffers* b) { delete b; }
 
 #define SCU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { *err = std::string(#expr) + ": " + cudaGetErrorString(e__); return 1; } } while (0)
 #define SNC(expr) do { ncclResult_t r__ = (expr); if (r__ != ncclSuccess) { *err = std::string(#expr) + ": " + NC->GetErrorString(r__); return 2; } } while (0)
+
+#include "lstm_batch.cuh"
+
+BatchBuffers* batch_buffers_new() { return new BatchBuffers(); }
+void batch_buffers_free(BatchBuffers* b) { delete b; }
 
 bool sync_supported(const ModelDev& m, const char** why) {
     if (m.model != MODEL_EWMA) { *why = "Parallelism::Synchronous with num_threads > 1 is implemented for the EWMA model only"; return false; }
