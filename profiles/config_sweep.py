@@ -11,9 +11,9 @@ PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if 
 CONFIGS = {  # kind, N, D, L, sequences, loss, optimizer, zipf
     "c1": ("ewma", 1683, 32, 32, 1 << 20, "bpr", "adagrad"),
     "c2": ("lstm", 1683, 32, 32, 1 << 20, "warp", "adagrad"),
-    "c3": ("lstm", 1_000_000, 64, 64, 1 << 18, "hinge", "adam"),
+    "c3": ("lstm", 1_000_000, 64, 64, 1 << 19, "hinge", "adam"),
     "c4": ("ewma", 50_000_000, 128, 128, 1 << 16, "bpr", "adagrad"),
-    "c5": ("lstm", 27_000, 256, 200, 1 << 15, "warp", "adagrad"),
+    "c5": ("lstm", 27_000, 256, 200, 1 << 17, "warp", "adagrad"),
 }
 LOSS = {"warp": pkg.Loss.WARP, "hinge": pkg.Loss.Hinge, "bpr": pkg.Loss.BPR}
 OPT = {"adagrad": pkg.Optimizer.Adagrad, "adam": pkg.Optimizer.Adam}

@@ -1449,6 +1449,11 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
     uint64_t sync_rounds = 0;
     const bool sync_mode = m->h.parallelism == SBR_PARALLELISM_SYNCHRONOUS && (P > 1 || g_world > 1) && sync_supported(m->dev, &why) &&
                            (int)(m->dev.gmask + 1) == (m->h.shard_world > 1 ? m->h.shard_world : 1);
+    if (m->h.parallelism == SBR_PARALLELISM_SYNCHRONOUS && (P > 1 || g_world > 1) && !sync_mode && !pl->use_batch)
+        // never fall back to the Hogwild schedule behind the caller's back (the reference default is Synchronous, lstm.rs:66)
+        return fail(SBR_ERR_INVALID_ARGUMENT, std::string("Parallelism::Synchronous is not available for this configuration: ") +
+                                                   (why ? why : "the item table's sharding does not match the process group") +
+                                                   " (use Parallelism::Asynchronous or num_threads = 1)");
     if (pl->dev.epochs > 0 && pl->use_batch) {
         if (!pl->batch) pl->batch = batch_buffers_new();
         std::string err;

@@ -759,7 +759,7 @@ size_t train_scratch_floats_per_warp(const ModelDev& m) {
 int train_auto_partitions(const ModelDev& m, int num_sms) {
     // EWMA / FFMA LSTM: resident warps per SM (registers / shared memory); tensor-core LSTM: 2 tiles of 128 per SM
     if (m.D == 32 && !m.exact) return num_sms * (m.opt == 1 ? 128 : 256);   // tile kernels: 2 x 128 partitions per SM (Adam records: 1 x 128)
-    if (m.model == MODEL_LSTM && m.D > 32) return m.exact ? num_sms * 8 : 16384;   // wide LSTM: rounds of the batched tensor-core engine
+    if (m.model == MODEL_LSTM && m.D > 32) return m.exact ? num_sms * 8 : (m.D == 64 ? 32768 : 16384);   // wide LSTM: rounds of the batched tensor-core engine
     int per_sm = m.model == MODEL_EWMA ? (m.D <= 64 ? 32 : 16) : 16;
     return num_sms * per_sm;
 }

@@ -249,7 +249,7 @@ __global__ void bl_keys_kernel(PlanDev pl, BatchDims bd, BatchPtrs bp, unsigned 
         unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull;
         if (t < bp.Tn[p]) {
             const uint32_t* ids = pl.item_ids + bp.base[p];
-            const uint32_t ord = (p << 17) | ((uint32_t)(bd.Tm1 - 1 - t) << 2);
+            const uint32_t ord = (p << 14) | ((uint32_t)(bd.Tm1 - 1 - t) << 2);   // partition (18 bits) | t descending (12 bits) | neg, out, in
             k0 = ((unsigned long long)__ldg(ids + t) << 32) | (ord | 2u);
             k1 = ((unsigned long long)__ldg(ids + t + 1) << 32) | (ord | 1u);
             k2 = ((unsigned long long)bp.neg_id[i] << 32) | (ord | 0u);
@@ -270,25 +270,30 @@ __global__ void bl_finish_kernel(PlanDev pl, BatchDims bd, BatchPtrs bp) {
 // One CTA = 256 threads: thread 0 streams tiles (cp.async.bulk -> 2-stage ring, mbarrier transaction counts), thread 32 issues
 // the tcgen05 MMAs (a stage is released by tcgen05.commit when the MMAs that read it have finished), then all eight warps run
 // the epilogue out of TMEM: warp w reads lanes 32 (w % 4) .., warps w and w + 4 split the columns.
+// With a single k-iteration (embedding_dim <= 64 forward) one stage is enough and two CTAs share an SM: the epilogue of one
+// overlaps the loads of the other.
 constexpr int kGemmThreads = 256;
 constexpr uint32_t kStageBytes = 3 * kTileBytes;            // A tile + two B tiles
-constexpr uint32_t kGemmSmem = 2 * kStageBytes + 4096 + 1024;   // + ones tile + barriers
+__host__ __device__ constexpr uint32_t gemm_smem_bytes(int nstage) { return (uint32_t)nstage * kStageBytes + 4096 + 1024; }   // + ones tile + barriers
 
 struct GemmSmem {
     uint8_t* stage[2];
     uint8_t* ones;
     uint64_t* full; uint64_t* empty; uint64_t* done; uint32_t* tmem_ptr;
+    int nstage;
 };
-__device__ __forceinline__ GemmSmem gemm_smem_carve(uint8_t* smem) {
+__device__ __forceinline__ GemmSmem gemm_smem_carve(uint8_t* smem, int nstage) {
     GemmSmem s;
-    s.stage[0] = smem; s.stage[1] = smem + kStageBytes; s.ones = smem + 2 * kStageBytes;
-    uint8_t* misc = smem + 2 * kStageBytes + 4096;
+    s.nstage = nstage;
+    s.stage[0] = smem; s.stage[1] = smem + (nstage - 1) * kStageBytes; s.ones = smem + nstage * kStageBytes;
+    uint8_t* misc = smem + nstage * kStageBytes + 4096;
     s.full = reinterpret_cast<uint64_t*>(misc); s.empty = s.full + 2; s.done = s.full + 4;
     s.tmem_ptr = reinterpret_cast<uint32_t*>(misc + 64);
     return s;
 }
+template <int COLS>
 __device__ __forceinline__ void gemm_setup(const GemmSmem& s) {
-    if (threadIdx.x < 32) tmem_alloc<512>(s.tmem_ptr);
+    if (threadIdx.x < 32) tmem_alloc<COLS>(s.tmem_ptr);
     if (threadIdx.x == 0) {
         mbar_init(s.full, 1); mbar_init(s.full + 1, 1); mbar_init(s.empty, 1); mbar_init(s.empty + 1, 1); mbar_init(s.done, 1);
         fence_mbar_init();
@@ -297,10 +302,11 @@ __device__ __forceinline__ void gemm_setup(const GemmSmem& s) {
     __syncthreads();
     tc_fence_after_sync();
 }
+template <int COLS>
 __device__ __forceinline__ void gemm_teardown(const GemmSmem& s) {
     tc_fence_before_sync();
     __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc<512>(*s.tmem_ptr);
+    if (threadIdx.x < 32) tmem_dealloc<COLS>(*s.tmem_ptr);
 }
 
 // MODE 0: A K-major, B MN-major (forward)   1: A K-major, B K-major (dz)   2: A MN-major, B MN-major (dW)
@@ -308,10 +314,11 @@ __device__ __forceinline__ void gemm_teardown(const GemmSmem& s) {
 template <int MODE, class TileFn>
 __device__ __forceinline__ void gemm_mainloop(const GemmSmem& s, int niter, TileFn tile_of, bool with_ones) {
     const int tid = threadIdx.x;
+    const int sh = s.nstage - 1;   // 1 or 2 stages: stage = it & sh, use count = it >> sh
     if (tid == 0) {
         for (int it = 0; it < niter; ++it) {
-            const int st = it & 1;
-            if (it >= 2) mbar_wait(s.empty + st, ((it >> 1) - 1) & 1);
+            const int st = it & sh;
+            if (it >= s.nstage) mbar_wait(s.empty + st, ((it >> sh) - 1) & 1);
             const uint8_t *A, *B0, *B1;
             tile_of(it, A, B0, B1);
             const uint32_t bar = smem_u32(s.full + st);
@@ -325,8 +332,8 @@ __device__ __forceinline__ void gemm_mainloop(const GemmSmem& s, int niter, Tile
         constexpr uint32_t idesc = make_idesc_bf16(128, 128, MODE == 2 ? 1 : 0, MODE == 1 ? 0 : 1);
         constexpr uint32_t idesc1 = make_idesc_bf16(128, 16, 1, 1);
         for (int it = 0; it < niter; ++it) {
-            const int st = it & 1;
-            mbar_wait(s.full + st, (it >> 1) & 1);
+            const int st = it & sh;
+            mbar_wait(s.full + st, (it >> sh) & 1);
             tc_fence_after_sync();
             const uint8_t *A, *B0, *B1;
             tile_of(it, A, B0, B1);
@@ -349,10 +356,16 @@ __device__ __forceinline__ void gemm_mainloop(const GemmSmem& s, int niter, Tile
 }
 
 // gates_t = Z_t . W (+ bias), LSTM cell (lstm.rs:293-298): CTA = row block x two gate blocks (64 cells)
-__global__ void __launch_bounds__(kGemmThreads, 1) bl_fwd_kernel(ModelDev m, BatchDims bd, BatchPtrs bp, int t) {
+__device__ __forceinline__ float bl_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float bl_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 1 / (1 + 2^(-x log2 e)) and 2 / (1 + 2^(-2 x log2 e)) - 1 on the MUFU units (saturate cleanly at both ends)
+__device__ __forceinline__ float bl_sigm(float x) { return bl_rcp(1.0f + bl_ex2(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float bl_tanh(float x) { return fmaf(2.0f, bl_rcp(1.0f + bl_ex2(-2.8853900817779268f * x)), -1.0f); }
+
+__global__ void __launch_bounds__(kGemmThreads, 2) bl_fwd_kernel(ModelDev m, BatchDims bd, BatchPtrs bp, int t) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const GemmSmem s = gemm_smem_carve(smem);
-    gemm_setup(s);
+    const GemmSmem s = gemm_smem_carve(smem, bd.KB > 1 ? 2 : 1);
+    gemm_setup<256>(s);
     const int pb = blockIdx.x, j0 = blockIdx.y * 2, nj = min(2, bd.NBLK - j0);
     const uint8_t* zt = bp.Z + ((size_t)t * bd.PB + pb) * bd.KB * kTileBytes;
     gemm_mainloop<0>(s, bd.KB, [&](int it, const uint8_t*& A, const uint8_t*& B0, const uint8_t*& B1) {
@@ -375,17 +388,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) bl_fwd_kernel(ModelDev m, Bat
         const int u0 = (j0 + jl) * 32 + cu * 8;
         const uint32_t cb = tl + jl * 128 + cu * 8;
         float pf[8], pi[8], pg[8], po[8], pc[8], ptc[8], hn[8];
-        tmem_ld8x4(cb, cb + bd.UB, cb + 2 * bd.UB, cb + 3 * bd.UB, pf, pi, pg, po);
         const float4 c0 = bp.C[(size_t)(u0 / 4) * bd.Ppad + r], c1 = bp.C[(size_t)(u0 / 4 + 1) * bd.Ppad + r];
+        tmem_ld8x4(cb, cb + bd.UB, cb + 2 * bd.UB, cb + 3 * bd.UB, pf, pi, pg, po);
         const float cprev[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        float bf[8], bi[8], bg[8], bo[8];
+#pragma unroll
+        for (int h4 = 0; h4 < 2; ++h4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(bias + u0) + h4), b = __ldg(reinterpret_cast<const float4*>(bias + D + u0) + h4);
+            const float4 cc = __ldg(reinterpret_cast<const float4*>(bias + 2 * D + u0) + h4), d = __ldg(reinterpret_cast<const float4*>(bias + 3 * D + u0) + h4);
+            bf[4 * h4] = a.x; bf[4 * h4 + 1] = a.y; bf[4 * h4 + 2] = a.z; bf[4 * h4 + 3] = a.w;
+            bi[4 * h4] = b.x; bi[4 * h4 + 1] = b.y; bi[4 * h4 + 2] = b.z; bi[4 * h4 + 3] = b.w;
+            bg[4 * h4] = cc.x; bg[4 * h4 + 1] = cc.y; bg[4 * h4 + 2] = cc.z; bg[4 * h4 + 3] = cc.w;
+            bo[4 * h4] = d.x; bo[4 * h4 + 1] = d.y; bo[4 * h4 + 2] = d.z; bo[4 * h4 + 3] = d.w;
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float f = sigmoidf_(pf[e] + __ldg(bias + u0 + e));
-            const float ig = coupled ? 1.0f - f : sigmoidf_(pi[e] + __ldg(bias + D + u0 + e));
-            const float gg = tanhf(pg[e] + __ldg(bias + 2 * D + u0 + e));
-            const float og = sigmoidf_(po[e] + __ldg(bias + 3 * D + u0 + e));
+            const float f = bl_sigm(pf[e] + bf[e]);
+            const float ig = coupled ? 1.0f - f : bl_sigm(pi[e] + bi[e]);
+            const float gg = bl_tanh(pg[e] + bg[e]);
+            const float og = bl_sigm(po[e] + bo[e]);
             const float cn = f * cprev[e] + ig * gg;
-            const float tcn = tanhf(cn);
+            const float tcn = bl_tanh(cn);
             pf[e] = f; pi[e] = ig; pg[e] = gg; po[e] = og; pc[e] = act ? cn : 0.0f; ptc[e] = tcn; hn[e] = act ? og * tcn : 0.0f;
         }
         bp.C[(size_t)(u0 / 4) * bd.Ppad + r] = make_float4(pc[0], pc[1], pc[2], pc[3]);
@@ -401,14 +424,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) bl_fwd_kernel(ModelDev m, Bat
             a[4 * gs] = pack_bf16x8(pc); a[5 * gs] = pack_bf16x8(ptc);
         }
     }
-    gemm_teardown(s);
+    gemm_teardown<256>(s);
 }
 
 // dz_t = delta_t . W^T: CTA = row block x two feature blocks; columns [0, D) -> dh_{t-1}, [D, 2D) -> entry of the input row
-__global__ void __launch_bounds__(kGemmThreads, 1) bl_dz_kernel(BatchDims bd, BatchPtrs bp, int t) {
+__global__ void __launch_bounds__(kGemmThreads, 2) bl_dz_kernel(BatchDims bd, BatchPtrs bp, int t) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const GemmSmem s = gemm_smem_carve(smem);
-    gemm_setup(s);
+    const GemmSmem s = gemm_smem_carve(smem, bd.NBLK > 1 ? 2 : 1);
+    gemm_setup<256>(s);
     const int pb = blockIdx.x, k0 = blockIdx.y * 2, nk = min(2, bd.KB - k0);
     const uint8_t* dt = bp.Dl + ((size_t)t * bd.PB + pb) * bd.NBLK * kTileBytes;
     gemm_mainloop<1>(s, bd.NBLK, [&](int it, const uint8_t*& A, const uint8_t*& B0, const uint8_t*& B1) {
@@ -436,17 +459,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) bl_dz_kernel(BatchDims bd, Ba
             *reinterpret_cast<float4*>(gin + (k - D) + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
     }
-    gemm_teardown(s);
+    gemm_teardown<256>(s);
 }
 
 // dW^T[gate block][features] += sum over (timestep, row block) delta^T . Z, bias gradient through a column of ones;
 // CTA = gate block x two feature blocks x a slice of the (t, row block) pairs; reduce-adds into the canonical dense layout
 __global__ void __launch_bounds__(kGemmThreads, 1) bl_dw_kernel(BatchDims bd, BatchPtrs bp, int nsplit) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const GemmSmem s = gemm_smem_carve(smem);
+    const GemmSmem s = gemm_smem_carve(smem, 2);
     for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x) reinterpret_cast<uint4*>(s.ones)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
     fence_async_smem();
-    gemm_setup(s);
+    gemm_setup<512>(s);
     const int j = blockIdx.x, k0 = blockIdx.y * 2, nk = min(2, bd.KB - k0), sp = blockIdx.z;
     const int total = bd.Tm1 * (int)bd.PB;
     const int lo = (int)((long long)total * sp / nsplit), hi = (int)((long long)total * (sp + 1) / nsplit);
@@ -479,7 +502,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) bl_dw_kernel(BatchDims bd, Ba
             if (valid) atomicAdd(bp.dWsum + (size_t)2 * D * 4 * D + g * D + u, v[0]);
         }
     }
-    gemm_teardown(s);
+    gemm_teardown<512>(s);
 }
 
 }  // namespace
@@ -493,7 +516,7 @@ bool batch_lstm_supported(const ModelDev& m, uint32_t P, const char** why) {
     if (m.model != MODEL_LSTM) { *why = "not an LSTM model"; return false; }
     if (m.D != 16 && m.D != 32 && m.D != 64 && m.D != 128 && m.D != 256) { *why = "embedding_dim must be 16, 32, 64, 128 or 256"; return false; }
     if (m.gmask != 0) { *why = "the batched LSTM engine needs an unsharded item table"; return false; }
-    if (P >= 32768 || m.T > 8192) { *why = "the batched LSTM engine takes fewer than 32768 partitions and sequences of at most 8192 items"; return false; }
+    if (P >= (1u << 18) || m.T > 4096) { *why = "the batched LSTM engine takes fewer than 262144 partitions and sequences of at most 4096 items"; return false; }
     return true;
 }
 
@@ -538,9 +561,10 @@ int run_batch_lstm(const ModelDev& m, PlanDev& pl, BatchBuffers& B, uint64_t num
     bp.C = static_cast<float4*>(B.C.p); bp.dzh = static_cast<float4*>(B.dzh.p); bp.grads = static_cast<float*>(B.grads.p);
     bp.bgrads = static_cast<float*>(B.bgrads.p); bp.neg_id = static_cast<uint32_t*>(B.neg_id.p); bp.Tn = static_cast<int*>(B.Tn.p);
     bp.base = static_cast<uint64_t*>(B.base.p); bp.dWsum = static_cast<float*>(B.dWsum.p); bp.ones = nullptr;
-    SCU(cudaFuncSetAttribute(bl_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-    SCU(cudaFuncSetAttribute(bl_dz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-    SCU(cudaFuncSetAttribute(bl_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    const uint32_t smem_fwd = gemm_smem_bytes(bd.KB > 1 ? 2 : 1), smem_dz = gemm_smem_bytes(bd.NBLK > 1 ? 2 : 1), smem_dw = gemm_smem_bytes(2);
+    SCU(cudaFuncSetAttribute(bl_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd));
+    SCU(cudaFuncSetAttribute(bl_dz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dz));
+    SCU(cudaFuncSetAttribute(bl_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dw));
     OptCfg o; o.lr = m.lr; o.l2 = m.l2; o.adam = m.opt == 1; o.c1 = 1.0f; o.c2 = 1.0f;
     const int warps_grid = (int)((bd.Ppad + 7) / 8);
     const dim3 g_fwd(bd.PB, (bd.NBLK + 1) / 2), g_dz(bd.PB, (bd.KB + 1) / 2);
@@ -561,16 +585,16 @@ int run_batch_lstm(const ModelDev& m, PlanDev& pl, BatchBuffers& B, uint64_t num
             BL_DISPATCH_D(D, bl_begin_kernel<kD><<<warps_grid, 256, 0, st>>>(m, pl, bd, bp, it));
             *launches += 2;
             for (int t = 0; t < bd.Tm1; ++t) {
-                bl_fwd_kernel<<<g_fwd, kGemmThreads, kGemmSmem, st>>>(m, bd, bp, t);
+                bl_fwd_kernel<<<g_fwd, kGemmThreads, smem_fwd, st>>>(m, bd, bp, t);
                 BL_DISPATCH_D(D, bl_score_kernel<kD><<<warps_grid, 256, 0, st>>>(m, pl, bd, bp, t));
                 *launches += 2;
             }
             for (int t = bd.Tm1 - 1; t >= 0; --t) {
                 bl_delta_kernel<<<delta_blocks, 256, 0, st>>>(bd, bp, t, m.variant == 1 ? 1 : 0, t == bd.Tm1 - 1 ? 1 : 0);
-                bl_dz_kernel<<<g_dz, kGemmThreads, kGemmSmem, st>>>(bd, bp, t);
+                bl_dz_kernel<<<g_dz, kGemmThreads, smem_dz, st>>>(bd, bp, t);
                 *launches += 2;
             }
-            bl_dw_kernel<<<g_dw, kGemmThreads, kGemmSmem, st>>>(bd, bp, nsplit);
+            bl_dw_kernel<<<g_dw, kGemmThreads, smem_dw, st>>>(bd, bp, nsplit);
             bl_keys_kernel<<<148 * 4, 256, 0, st>>>(pl, bd, bp, k_in, v_in);
             size_t tmp = B.cub_tmp.cap;
             SCU(cub::DeviceRadixSort::SortPairs(B.cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (int)nslots, 0, 64, st));

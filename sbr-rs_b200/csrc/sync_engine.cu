@@ -126,10 +126,10 @@ __global__ void __launch_bounds__(256) sync_gather_kernel(ModelDev m, int self, 
 
 // requester side: fused EWMA forward/backward of one sub-sequence per warp on the received rows (ewma.rs:266-352)
 template <int D>
-__global__ void __launch_bounds__(256) sync_ewma_compute_kernel(ModelDev m, PlanDev pl, uint32_t it, const float* __restrict__ rows,
-                                                                const float* __restrict__ biases, const uint32_t* __restrict__ pos_of_slot,
+__global__ void __launch_bounds__(256) sync_ewma_compute_kernel(ModelDev m, PlanDev pl, uint32_t it, float* __restrict__ rows,
+                                                                float* __restrict__ biases, const uint32_t* __restrict__ pos_of_slot,
                                                                 float* __restrict__ grads, float* __restrict__ bgrads,
-                                                                float* __restrict__ dalpha_sum) {
+                                                                float* __restrict__ dalpha_sum, uint32_t* __restrict__ own_rows) {
     constexpr int V = VecOf<D>::V;
     const int lane = threadIdx.x & 31;
     const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -153,7 +153,21 @@ __global__ void __launch_bounds__(256) sync_ewma_compute_kernel(ModelDev m, Plan
         for (int v = 0; v < V; ++v) s[v] = t == 0 ? x[v] : a[v] * s[v] + (1.0f - a[v]) * x[v];
         vec_store<D>(S_ + (size_t)t * D, lane, s);
         const float posv = warp_dot<D>(s, pv) + biases[pp];
-        const float ngs = warp_dot<D>(s, qv) + biases[pq];
+        float ngs = warp_dot<D>(s, qv) + biases[pq];
+        if (m.loss == 2 && own_rows) {
+            // WARP (sequence_model.rs:47-68) on one GPU: the requested row is candidate 0; further candidates are read from the
+            // table itself (nothing writes it before the round's apply stage) and the accepted one replaces the request
+            const uint64_t key = pl.keys[p], step = pl.step_ctr[p];
+            for (int j = 1; j < 5 && !(1.0f - posv + ngs > 0.0f); ++j) {
+                const uint32_t cand = draw_item(key, step, (uint32_t)t, (uint32_t)j, pl.neg_range);
+                row_load_cg<D>(item_rec(m, cand), lane, qv);
+                const float bq = __ldcg(reinterpret_cast<const float*>(bias_rec(m, cand)));
+                ngs = warp_dot<D>(s, qv) + bq;
+                vec_store<D>(rows + (size_t)pq * D, lane, qv);
+                if (lane == 0) { biases[pq] = bq; own_rows[pq] = cand; }
+                __syncwarp();
+            }
+        }
         float l, g;
         if (m.loss == 0) { const float sg = sigmoidf_(ngs - posv); l = sg; g = sg * (1.0f - sg); }
         else { const float vv = 1.0f + ngs - posv; l = vv > 0.0f ? vv : 0.0f; g = vv > 0.0f ? 1.0f : 0.0f; }
@@ -217,21 +231,54 @@ __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, c
                                                          const float* __restrict__ bgrads, size_t n, OptCfg o) {
     constexpr int V = VecOf<D>::V;
     const int lane = threadIdx.x & 31;
-    for (size_t j = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += (size_t)gridDim.x * (blockDim.x >> 5)) {
+    const size_t stride = (size_t)gridDim.x * (blockDim.x >> 5);
+    const int rec_lines = (int)((rec_floats(m) * 4 + 127) / 128), grad_lines = (D * 4 + 127) / 128;
+    for (size_t j = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += stride) {
+        // the warp's next entry: its record and gradient row travel towards L2 while this one is applied (one line per lane)
+        if (j + stride < n) {
+            const unsigned long long kn = keys[j + stride];
+            const uint32_t rn = (uint32_t)(kn >> 32);
+            if (rn != kInvalid) {
+                if (lane < rec_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(shard_bias_rec(m, self, rn)) + lane * 128));
+                else if (lane < rec_lines + grad_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(grads + (size_t)vals[j + stride] * D) + (lane - rec_lines) * 128));
+            }
+        }
         const uint32_t r = (uint32_t)(keys[j] >> 32);
         if (r == kInvalid) continue;                                 // unused slot (sorted to the end)
         if (j > 0 && (uint32_t)(keys[j - 1] >> 32) == r) continue;   // not the first entry of its row
+        // the row's record is read once, takes the entries of its run one after the other in registers (same arithmetic
+        // and order as one read-modify-write per entry), and is written back once
+        float* rec = shard_item_rec(m, self, r);
+        float w[V], s1[V], s2[V];
+        row_load_cg<D>(rec, lane, w);
+        row_load_cg<D>(rec + D, lane, s1);
+        if (o.adam) row_load_cg<D>(rec + 2 * D, lane, s2);
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool bias_dirty = false;
+        if (lane == 0) bq = __ldcg(shard_bias_rec(m, self, r));
         for (size_t e = j; e < n && (uint32_t)(keys[e] >> 32) == r; ++e) {
             const uint32_t src = vals[e];
             float g[V];
             vec_load<D>(grads + (size_t)src * D, lane, g);
-            update_row<D>(shard_item_rec(m, self, r), lane, g, o);
+            if (!o.adam) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) adagrad_elem(w[v], s1[v], g[v], o.lr, o.l2);
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) adam_elem(w[v], s1[v], s2[v], g[v], o);
+            }
             if (lane == 0) {
                 const float bg = bgrads[src];
-                if (bg == bg) update_bias(shard_bias_rec(m, self, r), bg, o);
+                if (bg == bg) {
+                    if (!o.adam) adagrad_elem(bq.x, bq.y, bg, o.lr, o.l2); else adam_elem(bq.x, bq.y, bq.z, bg, o);
+                    bias_dirty = true;
+                }
             }
-            __syncwarp();
         }
+        row_store_cg<D>(rec, lane, w);
+        row_store_cg<D>(rec + D, lane, s1);
+        if (o.adam) row_store_cg<D>(rec + 2 * D, lane, s2);
+        if (lane == 0 && bias_dirty) __stcg(shard_bias_rec(m, self, r), bq);
     }
 }
 
@@ -290,7 +337,7 @@ void batch_buffers_free(BatchBuffers* b) { delete b; }
 
 bool sync_supported(const ModelDev& m, const char** why) {
     if (m.model != MODEL_EWMA) { *why = "Parallelism::Synchronous with num_threads > 1 is implemented for the EWMA model only"; return false; }
-    if (m.loss == 2) { *why = "Parallelism::Synchronous does not support WARP (data-dependent resampling needs the live table)"; return false; }
+    if (m.loss == 2 && m.gmask != 0) { *why = "Parallelism::Synchronous with WARP needs the whole item table on one GPU (candidates are resampled against it)"; return false; }
     return true;
 }
 
@@ -375,7 +422,7 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
             sync_bucket_kernel<<<148 * 4, 256, 0, st>>>(m, req_id, nslots, 1, counts, counts + 8, send_row, pos_of_slot, req_ord, send_ord);
             *launches += 3;
             size_t scnt[8] = {0}, soff[8] = {0}, rcnt[8] = {0}, roff[8] = {0}, nown = 0;
-            const uint32_t* own_rows = send_row; const uint32_t* own_ords = send_ord; const float* rows_for_compute = nullptr; const float* bias_for_compute = nullptr;
+            const uint32_t* own_rows = send_row; const uint32_t* own_ords = send_ord; float* rows_for_compute = nullptr; float* bias_for_compute = nullptr;
             if (world > 1) {
                 SNC(NC->AllGather(counts, B.allcounts.p, 8, ncclUint32, comm, st));
                 SCU(cudaMemcpyAsync(B.h_counts, B.allcounts.p, (size_t)G * 8 * 4, cudaMemcpyDeviceToHost, st));
@@ -404,11 +451,11 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
                 SNC(exchange(own_rows_buf, rcnt, roff, B.rows_req.p, scnt, soff, (size_t)D * 4));
                 SNC(exchange(own_bias_buf, rcnt, roff, B.bias_req.p, scnt, soff, 4));
             }
-            rows_for_compute = static_cast<const float*>(B.rows_req.p); bias_for_compute = static_cast<const float*>(B.bias_req.p);
+            rows_for_compute = static_cast<float*>(B.rows_req.p); bias_for_compute = static_cast<float*>(B.bias_req.p);
             // 4. fused forward/backward on the received rows
             SYNC_DISPATCH_D(D, sync_ewma_compute_kernel<kD><<<grid_p, 256, 0, st>>>(m, pl, it, rows_for_compute, bias_for_compute, pos_of_slot,
                                                                                      static_cast<float*>(B.grads_req.p), static_cast<float*>(B.bgrads_req.p),
-                                                                                     static_cast<float*>(B.dalpha.p)));
+                                                                                     static_cast<float*>(B.dalpha.p), world == 1 ? send_row : nullptr));
             ++*launches;
             // 5. gradients to owners, sparse visits on the owner's shard
             const float* g_own = static_cast<const float*>(B.grads_req.p); const float* bg_own = static_cast<const float*>(B.bgrads_req.p);

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 def _build(pkg, kind, N, T, D, shards, loss, opt, threads=1, seed=bytes(range(3, 19))):
     H = pkg.lstm.Hyperparameters if kind == "lstm" else pkg.ewma.Hyperparameters
     h = (H(N, T).embedding_dim(D).learning_rate(0.05).l2_penalty(1e-3).loss(LOSSES[loss]).optimizer(OPTS[opt])
-         .num_epochs(2).num_threads(threads).from_seed(seed).virtual_shards(shards))
+         .num_epochs(2).num_threads(threads).parallelism(0).from_seed(seed).virtual_shards(shards))   # Parallelism::Asynchronous
     if kind == "lstm":
         h = h.lstm_variant(VARIANTS["normal"])
     return h.build()

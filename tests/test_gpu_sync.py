@@ -52,3 +52,48 @@ def test_synchronous_is_deterministic_and_learns(pkg):
         assert np.all(np.isfinite(m.get_parameter("item_embeddings")))
     assert losses[0][-1] < losses[0][0]
     assert abs(losses[0][0] - losses[1][0]) < 1e-3   # same schedule; only colliding rows inside a round may race
+
+
+@pytest.mark.parametrize("D,P", [(32, 4), (64, 6)])
+def test_synchronous_ewma_warp_matches_oracle(pkg, oracle, D, P):
+    """WARP under Parallelism::Synchronous on one GPU: the requested negative is candidate 0, further candidates are scored
+    against the round-start table (sequence_model.rs:47-68), the accepted one replaces the request before the apply stage."""
+    rng = np.random.default_rng(33)
+    N, T, U = 1_000_000, 10, 40
+    lens = rng.integers(3, 25, size=U)
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    ids = rng.integers(1, N, size=int(ptr[-1])).astype(np.uint64)
+    gm, om = make_pair(pkg, oracle, "ewma", N, T, D, loss="warp", optimizer="adagrad", lr=0.05, l2=1e-3, epochs=2, threads=P,
+                       parallelism="synchronous")
+    r = np.random.default_rng(3)
+    touched = np.unique(ids)
+    e = gm.get_parameter("item_embeddings").reshape(N, D)
+    e[touched] = (r.standard_normal((len(touched), D)) * 0.3).astype(np.float32)
+    gm.set_parameter("item_embeddings", e)
+    gm.set_parameter("item_biases", (r.standard_normal(N) * 0.8).astype(np.float32))   # spread biases: candidates do get rejected
+    gm.set_parameter("alpha", (r.standard_normal(D) * 0.5).astype(np.float32))
+    for n in om.param_names():
+        om.param(n)[:] = gm.get_parameter(n)
+    b0 = gm.get_parameter("item_biases").copy()
+    data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
+    gl = gm.fit(data)
+    rc, ol = om.fit(ptr, ids)
+    assert rc == 0
+    assert "round-synchronous" in gm.last_fit_stats()["kernel"]
+    diffs = max_abs_diff(gm, om, state_names(om, "adagrad"))
+    assert max(diffs.values()) <= 2e-4, diffs
+    assert abs(gl - ol) <= 1e-4 * max(1.0, abs(ol))
+    # the resampling did happen: more negative rows were visited than one per timestep could explain without rejections
+    moved = np.flatnonzero(om.param("item_biases") != b0)
+    assert len(moved) > len(touched)
+
+
+def test_synchronous_never_falls_back_to_hogwild_silently(pkg):
+    """A configuration the round-synchronous engines cannot run (WARP on a row-sharded table) is refused, not run asynchronously."""
+    rng = np.random.default_rng(1)
+    ptr = (np.arange(65) * 8).astype(np.uint64)
+    ids = rng.integers(1, 100, size=64 * 8).astype(np.uint64)
+    m = (pkg.ewma.Hyperparameters(100, 8).embedding_dim(32).loss(pkg.Loss.WARP).parallelism(pkg.Parallelism.Synchronous).num_threads(4)
+         .from_seed(bytes(range(16))).virtual_shards(2).build())
+    with pytest.raises(pkg.SbrError):
+        m.fit(pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=100))
