@@ -59,6 +59,51 @@ def gather_leg(pkg):
             "table_bytes": N * D * 4 * 2, "algorithmic_bytes_per_row": 8 * D + 4, "kernel": "gather_rows_kernel"}
 
 
+def sharded_c4_leg(pkg, torch, dist, rank, world, steps, warmup, barrier, max_over_ranks):
+    """BASELINE configs[3] / north_star's multi-GPU requirement: EWMA dim=128 seq=128 BPR Adagrad on a catalogue that is
+    ROW-SHARDED over the GPUs (item id % world; 6.25 M items = 6.5 GB of records per GPU, 50 M items at 8 GPUs: weak scaling),
+    trained by the round-synchronous engine (Parallelism::Synchronous): per round the requested (row, order) pairs, the rows
+    and the gradient rows cross NVLink as NCCL all-to-alls (grouped ncclSend/ncclRecv), optimizer state never moves.  Every
+    rank trains its own users; `value` = sub-sequences of all ranks / max-over-ranks wall time, device-resident plan."""
+    items_per_gpu, D4, T4, P4, rounds = 6_250_000, 128, 128, 4736, 8
+    N4 = items_per_gpu * world
+    S4 = P4 * rounds
+    rng = np.random.default_rng(4000 + rank)
+    ptr = np.arange(S4 + 1, dtype=np.uint64) * np.uint64(T4)
+    ids = rng.integers(1, N4, size=S4 * T4, dtype=np.uint64)
+    h = (pkg.ewma.Hyperparameters(N4, T4).embedding_dim(D4).learning_rate(0.05).l2_penalty(0.0).loss(pkg.Loss.BPR)
+         .optimizer(pkg.Optimizer.Adagrad).parallelism(pkg.Parallelism.Synchronous).num_epochs(1).num_threads(P4)
+         .from_seed(bytes(range(16))))
+    if world > 1:
+        h = h.shard(rank, world)
+    model = h.build()
+    plan = model.fit_plan(pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N4).upload())
+    for _ in range(max(1, warmup - 1)):
+        plan.run()
+    barrier()
+    t0 = time.perf_counter()
+    kms, ts = 0.0, 0
+    for _ in range(steps):
+        plan.run()
+        st = plan.stats()
+        kms += st["train_kernel_ms"]; ts += st["timesteps"]
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - t0)
+    st = plan.stats()
+    a_bytes = 60 * D4 + 52
+    peak = peaks()[0]
+    out = {"workload": "EWMA dim=128 seq=128 BPR Adagrad, item table row-sharded over %d GPU(s) (id %% world), %d items (BASELINE configs[3], weak-scaled: "
+                       "%d items per GPU)" % (world, N4, items_per_gpu),
+           "value": world * st["steps"] * steps / wall, "unit": "steps/s", "ms_per_step": wall / steps * 1e3,
+           "seqs_per_gpu_per_step": int(st["steps"]), "partitions_per_gpu": int(st["partitions"]), "rounds_per_step": rounds,
+           "kernel": st["kernel"], "gpu_launches_per_step": int(st["kernel_launches"]),
+           "per_gpu_hbm_frac": a_bytes * ts / (kms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_timestep": a_bytes,
+           "exchange": "NCCL grouped send/recv all-to-all of (row, order) pairs, rows + biases, gradient rows; two half-round pipelines overlap "
+                       "transfers with the gather / compute / apply kernels" if world > 1 else "none (one GPU owns every row)"}
+    del plan, model
+    return out
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -229,6 +274,10 @@ def main():
     hyper = hyper_factory()
     multi = os.environ.get("SBR_BENCH_MULTI", "replicas") if world > 1 else "single"
     sync = None
+    if world > 1:   # the library's own NCCL communicator (sbr_dist_init): replica all-reduce and the sharded engine's all-to-alls
+        uid = [pkg.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        pkg.dist_init(rank, world, uid[0])
     if multi == "shared":
         model = hyper.shard(rank, world).build()
         blobs = [None] * world
@@ -238,8 +287,12 @@ def main():
     else:
         model = hyper.build()
         if world > 1:
-            names = ["item_embeddings", "item_biases", "lstm_weights", "lstm_biases"]
-            sync = ReplicaSync(model, names + [n + ".s1" for n in names], torch, dist)
+            class LibSync:   # sbr_model_replica_sync: one ncclAllReduce on device buffers inside the library
+                bytes_per_sync = 0
+                def __call__(self):
+                    self.bytes_per_sync = model.replica_sync() or self.bytes_per_sync
+            sync = LibSync()
+            sync()           # records the common starting point
 
     # ---------------- device-resident arm: `value` ----------------
     data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=NUM_ITEMS).upload()
@@ -307,8 +360,6 @@ def main():
             st_ = model.last_fit_stats()
             h2d_, d2h_ = st_["h2d_bytes"], st_["d2h_bytes"]
             up_ms += st_["upload_ms"]; prep_ms += st_["host_prepare_ms"]
-            if sync:
-                h2d_ += sync.bytes_per_sync; d2h_ += sync.bytes_per_sync
             del c
         barrier()
         wall_ = max_over_ranks(time.perf_counter() - t0_)
@@ -320,6 +371,11 @@ def main():
     ids_pl[:] = ids; ptr_pl[:] = ptr
     e2e_value, h2d, d2h, e2e_upload_ms, e2e_host_ms = e2e_arm(ptr_pl, ids_pl)
     e2e_pageable = e2e_arm(ptr, ids)
+
+    del model
+    c4 = None
+    if os.environ.get("SBR_BENCH_C4", "1") != "0":
+        c4 = sharded_c4_leg(pkg, torch, dist, rank, world, args.steps, args.warmup, barrier, max_over_ranks)
 
     if rank == 0:
         peak, peak_kind = peaks()
@@ -346,7 +402,7 @@ def main():
                            parallelism=("hogwild partitions; one shared model, item table row-sharded over %d GPUs via NVLink peer access" % world)
                            if multi == "shared" else
                            ("hogwild partitions per GPU; full replica per GPU, deltas of parameters and Adagrad state summed over %d GPUs "
-                            "(one NCCL all-reduce of %d bytes) after every step" % (world, sync.bytes_per_sync)) if world > 1 else "hogwild partitions",
+                            "(one ncclAllReduce of %d bytes on device buffers inside the library) after every step" % (world, sync.bytes_per_sync)) if world > 1 else "hogwild partitions",
                            l2_policy="id stream (%d MiB/GPU) larger than L2; 215 KB item table is L2-resident by construction"
                                      % (S * SEQ_LEN * 4 >> 20)),
             "timesteps_per_s": value * (SEQ_LEN - 1),
@@ -361,6 +417,8 @@ def main():
                          "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind, "kernel": kernel_name,
                          "algorithmic_bytes_per_timestep": A_TRAIN_BYTES_PER_TIMESTEP},
         }
+        if c4:
+            out["sharded_c4"] = c4
         if zipf:
             out["zipf"] = zipf
         if world == 1:
@@ -376,6 +434,7 @@ def main():
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
+        pkg.dist_finalize()
         dist.destroy_process_group()
 
 

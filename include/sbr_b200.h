@@ -207,6 +207,12 @@ sbr_status sbr_hyper_shard(sbr_hyperparameters* h, int rank, int world);   /* wo
 sbr_status sbr_dist_unique_id(uint8_t out[128]);
 sbr_status sbr_dist_init(int rank, int world, const uint8_t id[128]);
 void sbr_dist_finalize(void);
+/* Data-parallel replicas of a small model (one full replica per GPU, every rank trains its own users): adds up what every
+ * rank changed since the previous call -- parameters and optimizer state of the item records and the dense weights -- with
+ * one ncclAllReduce on device buffers and applies the sum to the common starting point, so all replicas are identical again
+ * (the sum of all partitions' updates, as in one Hogwild run over all ranks' partitions, with a staleness of one call).
+ * The first call records the starting point.  Needs sbr_dist_init.  *bytes_reduced (optional): size of the all-reduce. */
+sbr_status sbr_model_replica_sync(sbr_model* m, size_t* bytes_reduced);
 /* Same sharded addressing with all shards in this process / on this device (used by single-GPU tests). */
 sbr_status sbr_hyper_virtual_shards(sbr_hyperparameters* h, int shards);
 size_t sbr_model_ipc_handle_size(void);

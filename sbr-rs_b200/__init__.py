@@ -44,7 +44,7 @@ EXPORTS = [
     "sbr_model_parameter_len", "sbr_model_get_parameter", "sbr_model_set_parameter", "sbr_model_get_num_updates",
     "sbr_model_set_num_updates", "sbr_model_get_rng_state", "sbr_model_set_rng_state", "sbr_model_free",
     "sbr_hyper_shard", "sbr_hyper_virtual_shards", "sbr_model_ipc_handle_size", "sbr_model_ipc_export",
-    "sbr_model_ipc_attach", "sbr_dist_unique_id", "sbr_dist_init", "sbr_dist_finalize",
+    "sbr_model_ipc_attach", "sbr_model_replica_sync", "sbr_dist_unique_id", "sbr_dist_init", "sbr_dist_finalize",
     "sbr_fit_plan_create", "sbr_fit_plan_run", "sbr_fit_plan_stats", "sbr_fit_plan_free", "sbr_model_last_fit_stats",
 ]
 
@@ -182,6 +182,7 @@ def lib():
     L.sbr_model_ipc_handle_size.restype = C.c_size_t
     L.sbr_model_ipc_export.argtypes = [vp, C.c_void_p]
     L.sbr_model_ipc_attach.argtypes = [vp, C.c_void_p]
+    L.sbr_model_replica_sync.argtypes = [vp, C.POINTER(C.c_size_t)]
     L.sbr_dist_unique_id.argtypes = [u8p]
     L.sbr_dist_init.argtypes = [C.c_int, C.c_int, u8p]
     L.sbr_dist_finalize.restype = None
@@ -640,6 +641,12 @@ class _Model:
     def restore(self, path):
         """overwrite parameters, optimizer state, rng and update counter from a checkpoint of the same shape"""
         _check(lib().sbr_model_restore(self._m, os.fsencode(path)))
+
+    def replica_sync(self):
+        """sbr_model_replica_sync: sum of all ranks' parameter / optimizer-state deltas applied to every replica; returns the bytes all-reduced."""
+        n = C.c_size_t()
+        _check(lib().sbr_model_replica_sync(self._m, C.byref(n)))
+        return n.value
 
     def ipc_export(self):
         buf = C.create_string_buffer(lib().sbr_model_ipc_handle_size())

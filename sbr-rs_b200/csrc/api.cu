@@ -295,6 +295,7 @@ struct sbr_model {
     bool attached = true;         // false between build() and sbr_model_ipc_attach() when shard_world > 1
     float* scratch_cache = nullptr; size_t scratch_cap = 0; bool scratch_busy = false;  // grow-only activation scratch
     uint8_t* h_stage = nullptr; size_t h_stage_cap = 0;   // grow-only pinned staging area of fit(): shuffled order | partition rngs | keys
+    float* replica_snap = nullptr; float* replica_delta = nullptr; size_t replica_n = 0;   // sbr_model_replica_sync: common starting point, delta buffer
     ~sbr_model() {
         for (int i = 0; i < 8; ++i) {
             if (own[i]) { if (dev.Es[i]) cudaFree(dev.Es[i]); }
@@ -304,6 +305,8 @@ struct sbr_model {
         if (own_dense) cudaFree(own_dense);
         if (scratch_cache) cudaFree(scratch_cache);
         if (h_stage) cudaFreeHost(h_stage);
+        if (replica_snap) cudaFree(replica_snap);
+        if (replica_delta) cudaFree(replica_delta);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -933,6 +936,65 @@ void sbr_dist_finalize(void) {
     g_rank = 0; g_world = 1;
 }
 
+}  // extern "C"
+namespace {
+// replicas: what this rank changed since the common starting point / the starting point plus everybody's changes
+__global__ void replica_delta_kernel(const float* __restrict__ a, size_t na, const float* __restrict__ b, size_t nb, const float* __restrict__ snap,
+                                     float* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < na + nb; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (i < na ? a[i] : b[i - na]) - snap[i];
+}
+__global__ void replica_apply_kernel(float* __restrict__ a, size_t na, float* __restrict__ b, size_t nb, float* __restrict__ snap,
+                                     const float* __restrict__ sum) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < na + nb; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = snap[i] + sum[i];
+        snap[i] = v;
+        if (i < na) a[i] = v; else b[i - na] = v;
+    }
+}
+}  // namespace
+extern "C" {
+
+// Data-parallel replicas of a small (L2-resident) model: every rank trains its own users on a full replica; this call makes
+// the replicas identical again by adding up what each of them changed -- the deltas of every parameter AND of the optimizer
+// state (item records, dense weights) since the last call are summed over the ranks with one ncclAllReduce on device buffers
+// and applied to the common starting point.  The first call only records the starting point (the replicas must be identical
+// then: same seed / same checkpoint).  Needs sbr_dist_init; the model must not be row-sharded.
+sbr_status sbr_model_replica_sync(sbr_model* m, size_t* bytes_reduced) {
+    if (!m) return fail(SBR_ERR_INVALID_ARGUMENT, "null model");
+    sbr_status s = require_device();
+    if (s) return s;
+    if (m->h.shard_world > 1 || m->dev.gmask != 0) return fail(SBR_ERR_INVALID_ARGUMENT, "replica sync needs an unsharded model");
+    std::lock_guard<std::mutex> lk(m->mu);
+    cudaStream_t st = m->stream;
+    const size_t na = (size_t)m->dev.N * rec_floats(m->dev), nb = 3 * m->dev.ndense, n = na + nb;
+    if (bytes_reduced) *bytes_reduced = 0;
+    if (!m->replica_snap || m->replica_n != n) {
+        if (m->replica_snap) { cudaFree(m->replica_snap); cudaFree(m->replica_delta); m->replica_snap = m->replica_delta = nullptr; }
+        CU(cudaMalloc(&m->replica_snap, n * sizeof(float)));
+        CU(cudaMalloc(&m->replica_delta, n * sizeof(float)));
+        m->replica_n = n;
+        CU(cudaMemcpyAsync(m->replica_snap, m->dev.Es[0], na * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(m->replica_snap + na, m->dev.dense, nb * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        return SBR_OK;
+    }
+    if (g_world <= 1) return SBR_OK;
+    if (!g_comm) return fail(SBR_ERR_NCCL, "sbr_model_replica_sync needs sbr_dist_init");
+    std::string why;
+    const NcclApi* nc = nccl_api(&why);
+    if (!nc) return fail(SBR_ERR_NCCL, why);
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    replica_delta_kernel<<<blocks, 256, 0, st>>>(m->dev.Es[0], na, m->dev.dense, nb, m->replica_snap, m->replica_delta);
+    ncclResult_t r = nc->AllReduce(m->replica_delta, m->replica_delta, n, ncclFloat, ncclSum, g_comm, st);
+    if (r != ncclSuccess) return fail(SBR_ERR_NCCL, std::string("ncclAllReduce: ") + nc->GetErrorString(r));
+    replica_apply_kernel<<<blocks, 256, 0, st>>>(m->dev.Es[0], na, m->dev.dense, nb, m->replica_snap, m->replica_delta);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    if (bytes_reduced) *bytes_reduced = n * sizeof(float);
+    return SBR_OK;
+}
+
 size_t sbr_model_ipc_handle_size(void) { return 2 * sizeof(cudaIpcMemHandle_t); }
 
 sbr_status sbr_model_ipc_export(const sbr_model* m, void* out) {
@@ -1336,7 +1398,7 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     pl->model = m; pl->nsub = nsub; pl->P = P; pl->n = n;
     {   // which engine: LSTM under Parallelism::Synchronous (any width), and the wide LSTMs with many partitions, run in rounds
         const char* why = nullptr;
-        const bool can = m->dev.model == MODEL_LSTM && g_world <= 1 && m->h.shard_world <= 1 && batch_lstm_supported(m->dev, (uint32_t)P, &why);
+        const bool can = m->dev.model == MODEL_LSTM && m->h.shard_world <= 1 && batch_lstm_supported(m->dev, (uint32_t)P, &why);
         const bool sync_lstm = m->dev.model == MODEL_LSTM && m->h.parallelism == SBR_PARALLELISM_SYNCHRONOUS && P > 1;
         if (sync_lstm && !can) { delete pl; return fail(SBR_ERR_INVALID_ARGUMENT, std::string("Parallelism::Synchronous LSTM fit: ") + (why ? why : "one process / unsharded table only")); }
         pl->use_batch = can && (sync_lstm || (m->dev.D > 32 && !m->dev.exact && P >= 128));

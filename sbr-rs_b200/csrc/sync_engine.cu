@@ -18,6 +18,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -58,6 +59,8 @@ __global__ void sync_shuffle_kernel(PlanDev pl) {
 // sequentially in exactly that order -- consecutive timesteps always share a row (out_{t-1} == in_t).
 __global__ void sync_request_kernel(ModelDev m, PlanDev pl, uint32_t it, uint64_t step_base, uint32_t part_base,
                                     uint32_t* __restrict__ req_id, uint32_t* __restrict__ req_ord) {
+    // step_base = rounds of this run already scheduled: the step counters in HBM move only at the end of a run, so that the
+    // requests of the next round can be built while the current one is still computing
     const int Tm1 = m.T - 1;
     const size_t total = (size_t)pl.P * Tm1;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -76,51 +79,62 @@ __global__ void sync_request_kernel(ModelDev m, PlanDev pl, uint32_t it, uint64_
     }
 }
 
-// bucket the requests by owner GPU (warp-aggregated): pass 0 counts, pass 1 scatters
-__global__ void sync_bucket_kernel(ModelDev m, const uint32_t* __restrict__ req_id, size_t nslots, int pass,
-                                   unsigned int* counts /*[G]*/, unsigned int* cursor /*[G]*/, uint32_t* __restrict__ send_row,
-                                   uint32_t* __restrict__ pos_of_slot, const uint32_t* __restrict__ req_ord, uint32_t* __restrict__ send_ord) {
+// bucket the requests by (half-round group, owner GPU), warp-aggregated: pass 0 counts, pass 1 scatters.  Group = which half
+// of the partitions the slot belongs to (the two halves of a round are exchanged and computed as two overlapping pipelines);
+// a group's entries for owner g sit at  goff[grp] + sum of the group's counts below g.  pos_of_slot is group-local.
+__global__ void sync_bucket_kernel(ModelDev m, const uint32_t* __restrict__ req_id, size_t nslots, size_t slots_grp0, size_t goff1, int ngrp, int pass,
+                                   unsigned int* counts /*[2G]*/, unsigned int* cursor /*[2G]*/, uint2* __restrict__ send_pair,
+                                   uint32_t* __restrict__ pos_of_slot, const uint32_t* __restrict__ req_ord) {
     const int G = (int)m.gmask + 1, lane = threadIdx.x & 31;
-    __shared__ unsigned int off[8];
+    __shared__ unsigned int off[16];
     if (pass == 1) {
-        if (threadIdx.x < 8) { unsigned int o = 0; for (int g = 0; g < (int)threadIdx.x && g < G; ++g) o += counts[g]; off[threadIdx.x] = o; }
+        if (threadIdx.x < 16) {
+            const int grp = threadIdx.x / 8, g = threadIdx.x % 8;
+            unsigned int o = 0;
+            for (int q = 0; q < g && q < G; ++q) o += counts[grp * G + q];
+            off[threadIdx.x] = o;
+        }
         __syncthreads();
     }
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t nround = (nslots + stride - 1) / stride * stride;  // keep warps converged for the ballots
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
         const uint32_t id = i < nslots ? req_id[i] : kInvalid;
-        const int owner = id == kInvalid ? -1 : (int)(id & m.gmask);
-        for (int g = 0; g < G; ++g) {
-            const unsigned mask = __ballot_sync(kFull, owner == g);
+        const int grp = (ngrp > 1 && i >= slots_grp0) ? 1 : 0;
+        const int bucket = id == kInvalid ? -1 : grp * G + (int)(id & m.gmask);
+        for (int b = 0; b < ngrp * G; ++b) {
+            const unsigned mask = __ballot_sync(kFull, bucket == b);
             if (!mask) continue;
             const int leader = __ffs(mask) - 1;
             unsigned int base = 0;
-            if (lane == leader) base = atomicAdd(pass == 0 ? &counts[g] : &cursor[g], (unsigned int)__popc(mask));
+            if (lane == leader) base = atomicAdd(pass == 0 ? &counts[b] : &cursor[b], (unsigned int)__popc(mask));
             base = __shfl_sync(kFull, base, leader);
-            if (pass == 1 && owner == g) {
-                const unsigned int pos = off[g] + base + (unsigned int)__popc(mask & ((1u << lane) - 1));
-                send_row[pos] = id >> m.gshift;
-                send_ord[pos] = req_ord[i];
+            if (pass == 1 && bucket == b) {
+                const unsigned int pos = off[(b / G) * 8 + b % G] + base + (unsigned int)__popc(mask & ((1u << lane) - 1));
+                send_pair[(b >= G ? goff1 : 0) + pos] = make_uint2(id >> m.gshift, req_ord[i]);
                 pos_of_slot[i] = pos;
             }
         }
-        if (pass == 1 && i < nslots && owner < 0) pos_of_slot[i] = kInvalid;
+        if (pass == 1 && i < nslots && bucket < 0) pos_of_slot[i] = kInvalid;
     }
 }
 
 // owner side: copy the requested rows (weights only) and biases out of the local shard, warp per request
+// Requests that came from this rank itself (entries [self_lo, self_lo + self_n) of the owner-side list) are written straight
+// into the requester-side buffers: they never travel through NCCL.
+struct SelfSeg { size_t lo, n; float* rows; float* bias; };
 template <int D>
-__global__ void __launch_bounds__(256) sync_gather_kernel(ModelDev m, int self, const uint32_t* __restrict__ rows, size_t n,
-                                                          float* __restrict__ out_rows, float* __restrict__ out_bias) {
+__global__ void __launch_bounds__(256) sync_gather_kernel(ModelDev m, int self, const uint2* __restrict__ pairs, size_t n,
+                                                          float* __restrict__ out_rows, float* __restrict__ out_bias, SelfSeg ss) {
     constexpr int V = VecOf<D>::V;
     const int lane = threadIdx.x & 31;
     for (size_t j = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += (size_t)gridDim.x * (blockDim.x >> 5)) {
-        const uint32_t r = rows[j];
+        const uint32_t r = pairs[j].x;
         float w[V];
         row_load_cg<D>(shard_item_rec(m, self, r), lane, w);
-        vec_store<D>(out_rows + j * D, lane, w);
-        if (lane == 0) out_bias[j] = __ldcg(reinterpret_cast<const float*>(shard_bias_rec(m, self, r)));
+        const bool mine = j >= ss.lo && j < ss.lo + ss.n;
+        vec_store<D>(mine ? ss.rows + (j - ss.lo) * D : out_rows + j * D, lane, w);
+        if (lane == 0) *(mine ? ss.bias + (j - ss.lo) : out_bias + j) = __ldcg(reinterpret_cast<const float*>(shard_bias_rec(m, self, r)));
     }
 }
 
@@ -129,11 +143,12 @@ template <int D>
 __global__ void __launch_bounds__(256) sync_ewma_compute_kernel(ModelDev m, PlanDev pl, uint32_t it, float* __restrict__ rows,
                                                                 float* __restrict__ biases, const uint32_t* __restrict__ pos_of_slot,
                                                                 float* __restrict__ grads, float* __restrict__ bgrads,
-                                                                float* __restrict__ dalpha_sum, uint32_t* __restrict__ own_rows) {
+                                                                float* __restrict__ dalpha_sum, uint2* __restrict__ own_pairs,
+                                                                uint32_t p_lo, uint32_t p_hi, uint64_t step_base) {
     constexpr int V = VecOf<D>::V;
     const int lane = threadIdx.x & 31;
-    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (p >= pl.P) return;
+    const uint32_t p = p_lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= p_hi) return;
     const int Tm1 = m.T - 1;
     const uint32_t sq = pl.order[(size_t)p * pl.n + it];
     const int Tn = (int)pl.seq_len[sq] - 1;
@@ -154,17 +169,17 @@ __global__ void __launch_bounds__(256) sync_ewma_compute_kernel(ModelDev m, Plan
         vec_store<D>(S_ + (size_t)t * D, lane, s);
         const float posv = warp_dot<D>(s, pv) + biases[pp];
         float ngs = warp_dot<D>(s, qv) + biases[pq];
-        if (m.loss == 2 && own_rows) {
+        if (m.loss == 2 && own_pairs) {
             // WARP (sequence_model.rs:47-68) on one GPU: the requested row is candidate 0; further candidates are read from the
             // table itself (nothing writes it before the round's apply stage) and the accepted one replaces the request
-            const uint64_t key = pl.keys[p], step = pl.step_ctr[p];
+            const uint64_t key = pl.keys[p], step = step_base + pl.step_ctr[p];
             for (int j = 1; j < 5 && !(1.0f - posv + ngs > 0.0f); ++j) {
                 const uint32_t cand = draw_item(key, step, (uint32_t)t, (uint32_t)j, pl.neg_range);
                 row_load_cg<D>(item_rec(m, cand), lane, qv);
                 const float bq = __ldcg(reinterpret_cast<const float*>(bias_rec(m, cand)));
                 ngs = warp_dot<D>(s, qv) + bq;
                 vec_store<D>(rows + (size_t)pq * D, lane, qv);
-                if (lane == 0) { biases[pq] = bq; own_rows[pq] = cand; }
+                if (lane == 0) { biases[pq] = bq; own_pairs[pq].x = cand; }
                 __syncwarp();
             }
         }
@@ -212,13 +227,17 @@ __global__ void __launch_bounds__(256) sync_ewma_compute_kernel(ModelDev m, Plan
         const float dal = da[v] * a[v] * (1.0f - a[v]);
         if (D >= 32 || lane < D) atomicAdd(dalpha_sum + (D < 32 ? lane : lane * V + v), dal);
     }
-    if (lane == 0) { pl.loss_acc[p] += loss_seq; pl.examples[p] += (unsigned long long)Tn; pl.step_ctr[p] += 1; }
+    if (lane == 0) { pl.loss_acc[p] += loss_seq; pl.examples[p] += (unsigned long long)Tn; }
 }
 
-__global__ void sync_keys_kernel(const uint32_t* __restrict__ rows, const uint32_t* __restrict__ ords, size_t n,
-                                 unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+__global__ void sync_advance_steps_kernel(PlanDev pl, uint64_t rounds) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < pl.P) pl.step_ctr[p] += rounds;
+}
+
+__global__ void sync_keys_kernel(const uint2* __restrict__ pairs, size_t n, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
-        keys[j] = ((unsigned long long)rows[j] << 32) | ords[j];
+        keys[j] = ((unsigned long long)pairs[j].x << 32) | pairs[j].y;
         vals[j] = (uint32_t)j;
     }
 }
@@ -228,7 +247,7 @@ __global__ void sync_keys_kernel(const uint32_t* __restrict__ rows, const uint32
 template <int D>
 __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, const unsigned long long* __restrict__ keys,
                                                          const uint32_t* __restrict__ vals, const float* __restrict__ grads,
-                                                         const float* __restrict__ bgrads, size_t n, OptCfg o) {
+                                                         const float* __restrict__ bgrads, size_t n, OptCfg o, SelfSeg ss) {
     constexpr int V = VecOf<D>::V;
     const int lane = threadIdx.x & 31;
     const size_t stride = (size_t)gridDim.x * (blockDim.x >> 5);
@@ -240,7 +259,11 @@ __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, c
             const uint32_t rn = (uint32_t)(kn >> 32);
             if (rn != kInvalid) {
                 if (lane < rec_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(shard_bias_rec(m, self, rn)) + lane * 128));
-                else if (lane < rec_lines + grad_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(grads + (size_t)vals[j + stride] * D) + (lane - rec_lines) * 128));
+                else if (lane < rec_lines + grad_lines) {
+                    const size_t sn = vals[j + stride];
+                    const float* gp = (sn >= ss.lo && sn < ss.lo + ss.n) ? ss.rows + (sn - ss.lo) * D : grads + sn * D;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(gp) + (lane - rec_lines) * 128));
+                }
             }
         }
         const uint32_t r = (uint32_t)(keys[j] >> 32);
@@ -257,9 +280,10 @@ __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, c
         bool bias_dirty = false;
         if (lane == 0) bq = __ldcg(shard_bias_rec(m, self, r));
         for (size_t e = j; e < n && (uint32_t)(keys[e] >> 32) == r; ++e) {
-            const uint32_t src = vals[e];
+            const size_t src = vals[e];
+            const bool mine = src >= ss.lo && src < ss.lo + ss.n;   // entries of this rank's own partitions: still in the requester-side buffers
             float g[V];
-            vec_load<D>(grads + (size_t)src * D, lane, g);
+            vec_load<D>(mine ? ss.rows + (src - ss.lo) * D : grads + src * D, lane, g);
             if (!o.adam) {
 #pragma unroll
                 for (int v = 0; v < V; ++v) adagrad_elem(w[v], s1[v], g[v], o.lr, o.l2);
@@ -268,7 +292,7 @@ __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, c
                 for (int v = 0; v < V; ++v) adam_elem(w[v], s1[v], s2[v], g[v], o);
             }
             if (lane == 0) {
-                const float bg = bgrads[src];
+                const float bg = mine ? ss.bias[src - ss.lo] : bgrads[src];
                 if (bg == bg) {
                     if (!o.adam) adagrad_elem(bq.x, bq.y, bg, o.lr, o.l2); else adam_elem(bq.x, bq.y, bq.z, bg, o);
                     bias_dirty = true;
@@ -317,11 +341,33 @@ struct Buf {
 
 }  // namespace
 
+// request side of a round (double-buffered: the next round's requests are built and counted while this one computes)
+struct ReqSet {
+    Buf req_id, req_ord, send_pair, pos_of_slot, counts, allcounts;
+    unsigned int* h_counts = nullptr;   // pinned [G][16]: every rank's (group, owner) counts
+    cudaEvent_t ready = nullptr;
+    ~ReqSet() { if (h_counts) cudaFreeHost(h_counts); if (ready) cudaEventDestroy(ready); }
+};
+// data side of one half-round group
+struct GrpBufs {
+    Buf recv_pair, rows_req, bias_req, rows_own, bias_own, grads_req, bgrads_req, grads_own, bgrads_own, keys_in, keys_out, vals_in, vals_out, cub_tmp;
+    size_t cap_own = 0;
+    cudaEvent_t ev_gather = nullptr, ev_compute = nullptr, ev_apply = nullptr;
+    ~GrpBufs() { for (cudaEvent_t e : {ev_gather, ev_compute, ev_apply}) if (e) cudaEventDestroy(e); }
+};
 struct SyncBuffers {
-    Buf req_id, req_ord, send_row, send_ord, pos_of_slot, counts, allcounts, recv_row, recv_ord, keys_in, keys_out, vals_in, vals_out, cub_tmp, rows_req, bias_req, rows_own, bias_own, grads_req, bgrads_req,
-        grads_own, bgrads_own, dalpha;
-    unsigned int* h_counts = nullptr;  // pinned [G*G + G]
-    ~SyncBuffers() { if (h_counts) cudaFreeHost(h_counts); }
+    ReqSet rs[2];
+    GrpBufs grp[2];
+    Buf dalpha, scal;
+    unsigned int* h_scal = nullptr;     // pinned scalar for the round-count agreement
+    cudaStream_t s_b = nullptr, s_req = nullptr;
+    cudaEvent_t ev_round = nullptr, ev_consumed = nullptr;
+    ~SyncBuffers() {
+        if (h_scal) cudaFreeHost(h_scal);
+        if (s_b) cudaStreamDestroy(s_b);
+        if (s_req) cudaStreamDestroy(s_req);
+        for (cudaEvent_t e : {ev_round, ev_consumed}) if (e) cudaEventDestroy(e);
+    }
 };
 
 SyncBuffers* sync_buffers_new() { return new SyncBuffers(); }
@@ -343,143 +389,233 @@ bool sync_supported(const ModelDev& m, const char** why) {
 
 size_t sync_scratch_floats_per_partition(const ModelDev& m) { return (((size_t)m.T * m.D + m.T) + 31) / 32 * 32; }
 
-// returns 0 ok, 1 cuda error, 2 nccl error, 3 capacity error.  `comm` may be null when world == 1.
+// returns 0 ok, 1 cuda error, 2 nccl error.  `comm` may be null when world == 1.
+//
+// One round on G GPUs (G == 1: the exchanges are the identity and there is one group):
+//   request stream : ids + uniform negatives of the NEXT round, bucketed by (group, owner); counts all-gathered and copied to
+//                    the host while the current round runs -- the host never waits on the critical path
+//   group A / B    : the two halves of the partitions, each a pipeline on its own stream:
+//                      (row, order) pairs --all-to-all--> owners gather rows + biases from their shard
+//                      rows + biases      --all-to-all--> fused EWMA forward/backward on the received rows
+//                      gradient rows      --all-to-all--> owners sort by (row, reference order) and apply, A before B
+//                    NCCL serialises the transfers of one communicator, so A's transfers overlap B's kernels and vice versa.
+//   dense          : all-reduce of the round-summed alpha gradient, one step on every replica.
 int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, int rank, int world, uint64_t num_updates,
                   cudaStream_t st, int* launches, uint64_t* rounds_out, std::string* err) {
     ncclComm_t comm = static_cast<ncclComm_t>(comm_v);
     const NcclApi* NC = nullptr;
     if (world > 1) { NC = nccl_api(err); if (!NC) return 2; }
     const int G = world, D = m.D, Tm1 = m.T - 1;
+    const int NGRP = (world > 1 && pl.P >= 2) ? 2 : 1;
+    const uint32_t p_split = NGRP == 2 ? pl.P / 2 : pl.P;                  // group 0 = partitions [0, p_split)
     const size_t nslots = (size_t)pl.P * Tm1 * 3;
-    // Rows other ranks may request from this shard per round.  The usual load is ~nslots; a skewed id distribution (popular
-    // ids in one residue class mod world) can send up to world * nslots rows to one owner, so the owner-side buffers GROW
-    // when a round needs more (the stream is idle at that point: the counts were just read back).
-    size_t cap_own = 0;
-    auto ensure_own = [&](size_t need) -> int {
-        if (need <= cap_own) return 0;
-        cap_own = need;
-        SCU(B.keys_in.ensure(cap_own * 8)); SCU(B.keys_out.ensure(cap_own * 8)); SCU(B.vals_in.ensure(cap_own * 4)); SCU(B.vals_out.ensure(cap_own * 4));
+    const size_t slots_grp[2] = {(size_t)p_split * Tm1 * 3, nslots - (size_t)p_split * Tm1 * 3};
+    if (!B.s_b) { SCU(cudaStreamCreateWithFlags(&B.s_b, cudaStreamNonBlocking)); SCU(cudaStreamCreateWithFlags(&B.s_req, cudaStreamNonBlocking)); }
+    if (!B.ev_round) { SCU(cudaEventCreateWithFlags(&B.ev_round, cudaEventDisableTiming)); SCU(cudaEventCreateWithFlags(&B.ev_consumed, cudaEventDisableTiming)); }
+    if (!B.h_scal) SCU(cudaHostAlloc(&B.h_scal, 64, cudaHostAllocDefault));
+    SCU(B.scal.ensure(64)); SCU(B.dalpha.ensure(m.ndense * 4));
+    for (ReqSet& r : B.rs) {
+        SCU(r.req_id.ensure(nslots * 4)); SCU(r.req_ord.ensure(nslots * 4)); SCU(r.send_pair.ensure(nslots * 8)); SCU(r.pos_of_slot.ensure(nslots * 4));
+        SCU(r.counts.ensure(128)); SCU(r.allcounts.ensure(8 * 16 * 4));
+        if (!r.h_counts) SCU(cudaHostAlloc(&r.h_counts, 8 * 16 * sizeof(unsigned int), cudaHostAllocDefault));
+        if (!r.ready) SCU(cudaEventCreateWithFlags(&r.ready, cudaEventDisableTiming));
+    }
+    // Rows other ranks may request from this shard per round and group.  The usual load is ~ the group's own slot count; a
+    // skewed id distribution (popular ids in one residue class mod world) can send up to world x that to one owner, so the
+    // owner-side buffers GROW when a round needs more (both pipelines are drained first).
+    auto ensure_own = [&](GrpBufs& g, size_t need) -> int {
+        if (need <= g.cap_own) return 0;
+        SCU(cudaDeviceSynchronize());
+        g.cap_own = need;
+        SCU(g.keys_in.ensure(need * 8)); SCU(g.keys_out.ensure(need * 8)); SCU(g.vals_in.ensure(need * 4)); SCU(g.vals_out.ensure(need * 4));
         size_t cub_bytes = 0;
         SCU(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<unsigned long long*>(nullptr), static_cast<unsigned long long*>(nullptr),
-                                            static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), (int)cap_own, 0, 64, st));
-        SCU(B.cub_tmp.ensure(cub_bytes));
+                                            static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), (int)need, 0, 64, st));
+        SCU(g.cub_tmp.ensure(cub_bytes));
         if (world > 1) {
-            SCU(B.recv_row.ensure(cap_own * 4)); SCU(B.recv_ord.ensure(cap_own * 4)); SCU(B.rows_own.ensure(cap_own * D * 4)); SCU(B.bias_own.ensure(cap_own * 4));
-            SCU(B.grads_own.ensure(cap_own * D * 4)); SCU(B.bgrads_own.ensure(cap_own * 4));
+            SCU(g.recv_pair.ensure(need * 8)); SCU(g.rows_own.ensure(need * D * 4)); SCU(g.bias_own.ensure(need * 4));
+            SCU(g.grads_own.ensure(need * D * 4)); SCU(g.bgrads_own.ensure(need * 4));
         }
         return 0;
     };
-    SCU(B.req_id.ensure(nslots * 4)); SCU(B.send_row.ensure(nslots * 4)); SCU(B.pos_of_slot.ensure(nslots * 4));
-    SCU(B.req_ord.ensure(nslots * 4)); SCU(B.send_ord.ensure(nslots * 4));
-    if (int rc = ensure_own(world == 1 ? nslots : nslots * 3 / 2 + 4096)) return rc;
-    SCU(B.counts.ensure(64)); SCU(B.allcounts.ensure(8 * 8 * 4));
-    SCU(B.rows_req.ensure(nslots * D * 4)); SCU(B.bias_req.ensure(nslots * 4));
-    SCU(B.grads_req.ensure(nslots * D * 4)); SCU(B.bgrads_req.ensure(nslots * 4));
-    SCU(B.dalpha.ensure(m.ndense * 4));
-    if (!B.h_counts) SCU(cudaHostAlloc(&B.h_counts, (8 * 8 + 8) * sizeof(unsigned int), cudaHostAllocDefault));
+    for (int q = 0; q < NGRP; ++q) {
+        GrpBufs& g = B.grp[q];
+        SCU(g.rows_req.ensure(slots_grp[q] * D * 4)); SCU(g.bias_req.ensure(slots_grp[q] * 4));
+        SCU(g.grads_req.ensure(slots_grp[q] * D * 4)); SCU(g.bgrads_req.ensure(slots_grp[q] * 4));
+        if (int rc = ensure_own(g, world == 1 ? slots_grp[q] : slots_grp[q] * 3 / 2 + 4096)) return rc;
+        for (cudaEvent_t* e : {&g.ev_gather, &g.ev_compute, &g.ev_apply}) if (!*e) SCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
     SCU(cudaMemsetAsync(B.dalpha.p, 0, m.ndense * 4, st));
-    unsigned int* counts = static_cast<unsigned int*>(B.counts.p);       // [0..8) counts, [8..16) cursors
-    uint32_t* req_id = static_cast<uint32_t*>(B.req_id.p);
-    uint32_t* send_row = static_cast<uint32_t*>(B.send_row.p);
-    uint32_t* pos_of_slot = static_cast<uint32_t*>(B.pos_of_slot.p);
-    uint32_t* req_ord = static_cast<uint32_t*>(B.req_ord.p);
-    uint32_t* send_ord = static_cast<uint32_t*>(B.send_ord.p);
     OptCfg o; o.lr = m.lr; o.l2 = m.l2; o.adam = m.opt == 1; o.c1 = 1.0f; o.c2 = 1.0f;
-    const int grid_p = (int)((pl.P + 7) / 8);
+    cudaStream_t gst[2] = {st, B.s_b};
     uint64_t rounds_done = 0;
 
-    auto exchange = [&](const void* sendbuf, const size_t* scnt, const size_t* soff, void* recvbuf, const size_t* rcnt, const size_t* roff,
-                        size_t elem) -> ncclResult_t {
+    // every rank must run the same number of rounds (collectives inside): the ranks agree on the smallest partition length
+    uint32_t n_rounds = pl.n;
+    if (world > 1) {
+        unsigned int* d_scal = static_cast<unsigned int*>(B.scal.p);
+        B.h_scal[0] = pl.n;
+        SCU(cudaMemcpyAsync(d_scal, B.h_scal, 4, cudaMemcpyHostToDevice, st));
+        SNC(NC->AllReduce(d_scal, d_scal, 1, ncclUint32, ncclMin, comm, st));
+        SCU(cudaMemcpyAsync(B.h_scal, d_scal, 4, cudaMemcpyDeviceToHost, st));
+        SCU(cudaStreamSynchronize(st));
+        n_rounds = B.h_scal[0];
+    }
+    *rounds_out = (uint64_t)n_rounds * (uint64_t)pl.epochs;
+
+    // requests of round `it` into set `r` on the request stream (after `after` has happened: the epoch shuffle / the host
+    // having consumed the set's previous counts is implied by program order)
+    auto stage_requests = [&](ReqSet& r, uint32_t it, uint64_t step_base, cudaEvent_t after) -> int {
+        cudaStream_t sr = B.s_req;
+        if (after) SCU(cudaStreamWaitEvent(sr, after, 0));
+        unsigned int* counts = static_cast<unsigned int*>(r.counts.p);       // [0..16) counts, [16..32) cursors
+        SCU(cudaMemsetAsync(counts, 0, 128, sr));
+        uint32_t* req_id = static_cast<uint32_t*>(r.req_id.p); uint32_t* req_ord = static_cast<uint32_t*>(r.req_ord.p);
+        sync_request_kernel<<<148 * 8, 256, 0, sr>>>(m, pl, it, step_base, (uint32_t)rank * pl.P, req_id, req_ord);
+        for (int pass = 0; pass < 2; ++pass)
+            sync_bucket_kernel<<<148 * 4, 256, 0, sr>>>(m, req_id, nslots, slots_grp[0], slots_grp[0], NGRP, pass, counts, counts + 16,
+                                                        static_cast<uint2*>(r.send_pair.p), static_cast<uint32_t*>(r.pos_of_slot.p), req_ord);
+        *launches += 3;
+        if (world > 1) {
+            SNC(NC->AllGather(counts, r.allcounts.p, 16, ncclUint32, comm, sr));
+            SCU(cudaMemcpyAsync(r.h_counts, r.allcounts.p, (size_t)G * 16 * 4, cudaMemcpyDeviceToHost, sr));
+        } else SCU(cudaMemcpyAsync(r.h_counts, counts, 16 * 4, cudaMemcpyDeviceToHost, sr));
+        SCU(cudaEventRecord(r.ready, sr));
+        return 0;
+    };
+    auto exchange = [&](cudaStream_t s, const void* sendbuf, const size_t* scnt, const size_t* soff, void* recvbuf, const size_t* rcnt, const size_t* roff, size_t elem,
+                        const void* sendbuf2, void* recvbuf2, size_t elem2, bool skip_self) -> ncclResult_t {
         ncclResult_t r = NC->GroupStart();
         if (r != ncclSuccess) return r;
         for (int g = 0; g < G && r == ncclSuccess; ++g) {
-            if (scnt[g]) r = NC->Send(static_cast<const char*>(sendbuf) + soff[g] * elem, scnt[g] * elem, ncclChar, g, comm, st);
-            if (r == ncclSuccess && rcnt[g]) r = NC->Recv(static_cast<char*>(recvbuf) + roff[g] * elem, rcnt[g] * elem, ncclChar, g, comm, st);
+            if (g == rank && skip_self) continue;
+            if (scnt[g]) r = NC->Send(static_cast<const char*>(sendbuf) + soff[g] * elem, scnt[g] * elem, ncclChar, g, comm, s);
+            if (r == ncclSuccess && rcnt[g]) r = NC->Recv(static_cast<char*>(recvbuf) + roff[g] * elem, rcnt[g] * elem, ncclChar, g, comm, s);
+            if (sendbuf2 && r == ncclSuccess && scnt[g]) r = NC->Send(static_cast<const char*>(sendbuf2) + soff[g] * elem2, scnt[g] * elem2, ncclChar, g, comm, s);
+            if (sendbuf2 && r == ncclSuccess && rcnt[g]) r = NC->Recv(static_cast<char*>(recvbuf2) + roff[g] * elem2, rcnt[g] * elem2, ncclChar, g, comm, s);
         }
         const ncclResult_t re = NC->GroupEnd();   // the group is always closed, also after a failed Send / Recv
         return r != ncclSuccess ? r : re;
     };
 
-    // every rank must run the same number of rounds (collectives inside): the ranks agree on the smallest partition length
-    uint32_t n_rounds = pl.n;
-    if (world > 1) {
-        B.h_counts[64] = pl.n;
-        SCU(cudaMemcpyAsync(counts, &B.h_counts[64], 4, cudaMemcpyHostToDevice, st));
-        SNC(NC->AllReduce(counts, counts, 1, ncclUint32, ncclMin, comm, st));
-        SCU(cudaMemcpyAsync(&B.h_counts[64], counts, 4, cudaMemcpyDeviceToHost, st));
-        SCU(cudaStreamSynchronize(st));
-        n_rounds = B.h_counts[64];
-    }
-    *rounds_out = (uint64_t)n_rounds * (uint64_t)pl.epochs;
+    // SBR_SYNC_TRACE=1: CUDA-event timeline of round 2 on stderr (which stage of which pipeline ends when)
+    const bool trace = getenv("SBR_SYNC_TRACE") != nullptr;
+    std::vector<std::pair<std::string, cudaEvent_t>> tr;
+    auto mark = [&](const char* name, int q, cudaStream_t s, bool on) {
+        if (!on) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
+        tr.emplace_back(std::string(name) + (q == 0 ? " A" : q == 1 ? " B" : ""), e);
+    };
+    int cur = 0;
     for (int ep = 0; ep < pl.epochs; ++ep) {
         sync_shuffle_kernel<<<(pl.P + 127) / 128, 128, 0, st>>>(pl);
         ++*launches;
+        SCU(cudaEventRecord(B.ev_consumed, st));
+        if (n_rounds) if (int rc = stage_requests(B.rs[cur], 0, rounds_done, B.ev_consumed)) return rc;
         for (uint32_t it = 0; it < n_rounds; ++it, ++rounds_done) {
-            // 1. requests + bucketing by owner
-            SCU(cudaMemsetAsync(counts, 0, 64, st));
-            sync_request_kernel<<<148 * 8, 256, 0, st>>>(m, pl, it, 0, (uint32_t)rank * pl.P, req_id, req_ord);
-            sync_bucket_kernel<<<148 * 4, 256, 0, st>>>(m, req_id, nslots, 0, counts, counts + 8, send_row, pos_of_slot, req_ord, send_ord);
-            sync_bucket_kernel<<<148 * 4, 256, 0, st>>>(m, req_id, nslots, 1, counts, counts + 8, send_row, pos_of_slot, req_ord, send_ord);
-            *launches += 3;
-            size_t scnt[8] = {0}, soff[8] = {0}, rcnt[8] = {0}, roff[8] = {0}, nown = 0;
-            const uint32_t* own_rows = send_row; const uint32_t* own_ords = send_ord; float* rows_for_compute = nullptr; float* bias_for_compute = nullptr;
-            if (world > 1) {
-                SNC(NC->AllGather(counts, B.allcounts.p, 8, ncclUint32, comm, st));
-                SCU(cudaMemcpyAsync(B.h_counts, B.allcounts.p, (size_t)G * 8 * 4, cudaMemcpyDeviceToHost, st));
-                SCU(cudaStreamSynchronize(st));
+            ReqSet& R = B.rs[cur];
+            SCU(cudaEventSynchronize(R.ready));     // counts of this round on the host (enqueued one round ago)
+            size_t scnt[2][8] = {}, soff[2][8] = {}, rcnt[2][8] = {}, roff[2][8] = {}, nown[2] = {0, 0};
+            for (int q = 0; q < NGRP; ++q) {
                 size_t so = 0, ro = 0;
                 for (int g = 0; g < G; ++g) {
-                    scnt[g] = B.h_counts[rank * 8 + g]; soff[g] = so; so += scnt[g];
-                    rcnt[g] = B.h_counts[g * 8 + rank]; roff[g] = ro; ro += rcnt[g];
+                    scnt[q][g] = R.h_counts[(world > 1 ? rank * 16 : 0) + q * G + g]; soff[q][g] = so; so += scnt[q][g];
+                    rcnt[q][g] = world > 1 ? R.h_counts[g * 16 + q * G + rank] : scnt[q][g]; roff[q][g] = ro; ro += rcnt[q][g];
                 }
-                nown = ro;
-                if (int rc = ensure_own(nown)) return rc;
-                // 2. ids to owners
-                SNC(exchange(send_row, scnt, soff, B.recv_row.p, rcnt, roff, 4));
-                SNC(exchange(send_ord, scnt, soff, B.recv_ord.p, rcnt, roff, 4));
-                own_rows = static_cast<const uint32_t*>(B.recv_row.p); own_ords = static_cast<const uint32_t*>(B.recv_ord.p);
-            } else {
-                SCU(cudaMemcpyAsync(B.h_counts, counts, 4, cudaMemcpyDeviceToHost, st));
-                SCU(cudaStreamSynchronize(st));
-                nown = B.h_counts[0];
+                nown[q] = ro;
+                if (int rc = ensure_own(B.grp[q], nown[q])) return rc;
             }
-            // 3. owners gather, rows travel back
-            float* own_rows_buf = static_cast<float*>(world > 1 ? B.rows_own.p : B.rows_req.p);
-            float* own_bias_buf = static_cast<float*>(world > 1 ? B.bias_own.p : B.bias_req.p);
-            if (nown) { SYNC_DISPATCH_D(D, sync_gather_kernel<kD><<<148 * 8, 256, 0, st>>>(m, rank, own_rows, nown, own_rows_buf, own_bias_buf)); ++*launches; }
-            if (world > 1) {
-                SNC(exchange(own_rows_buf, rcnt, roff, B.rows_req.p, scnt, soff, (size_t)D * 4));
-                SNC(exchange(own_bias_buf, rcnt, roff, B.bias_req.p, scnt, soff, 4));
+            // both pipelines start once the previous round's table is final and the epoch shuffle (stream `st`) has run
+            if (NGRP == 2) { SCU(cudaEventRecord(B.ev_consumed, st)); SCU(cudaStreamWaitEvent(gst[1], B.ev_consumed, 0)); }
+            if (rounds_done > 0 && NGRP == 2) SCU(cudaStreamWaitEvent(gst[0], B.ev_round, 0));
+            const bool tron = trace && rounds_done == 2;
+            mark("start", 0, gst[0], tron); mark("start", 1, gst[NGRP - 1], tron && NGRP == 2);
+            const uint2* send_pair = static_cast<const uint2*>(R.send_pair.p);
+            const uint32_t* pos_of_slot = static_cast<const uint32_t*>(R.pos_of_slot.p);
+            const uint2* own_pairs[2];
+            // 1. (row, order) pairs to the owners; owners gather
+            for (int q = 0; q < NGRP; ++q) {
+                GrpBufs& g = B.grp[q];
+                const uint2* sp = send_pair + (q ? slots_grp[0] : 0);
+                own_pairs[q] = sp;
+                if (world > 1) {
+                    SNC(exchange(gst[q], sp, scnt[q], soff[q], g.recv_pair.p, rcnt[q], roff[q], 8, nullptr, nullptr, 0, false));
+                    own_pairs[q] = static_cast<const uint2*>(g.recv_pair.p);
+                    mark("pairs exchanged", q, gst[q], tron);
+                }
+                float* own_rows_buf = static_cast<float*>(world > 1 ? g.rows_own.p : g.rows_req.p);
+                float* own_bias_buf = static_cast<float*>(world > 1 ? g.bias_own.p : g.bias_req.p);
+                // this rank's own requests (owner-side entries [roff[rank], + rcnt[rank])  ==  requester-side entries [soff[rank], ..))
+                SelfSeg ss_rows; ss_rows.lo = roff[q][rank]; ss_rows.n = rcnt[q][rank];
+                ss_rows.rows = static_cast<float*>(g.rows_req.p) + soff[q][rank] * D; ss_rows.bias = static_cast<float*>(g.bias_req.p) + soff[q][rank];
+                if (nown[q]) { SYNC_DISPATCH_D(D, sync_gather_kernel<kD><<<148 * 8, 256, 0, gst[q]>>>(m, rank, own_pairs[q], nown[q], own_rows_buf, own_bias_buf, ss_rows)); ++*launches; }
+                SCU(cudaEventRecord(g.ev_gather, gst[q]));
+                mark("gathered", q, gst[q], tron);
             }
-            rows_for_compute = static_cast<float*>(B.rows_req.p); bias_for_compute = static_cast<float*>(B.bias_req.p);
-            // 4. fused forward/backward on the received rows
-            SYNC_DISPATCH_D(D, sync_ewma_compute_kernel<kD><<<grid_p, 256, 0, st>>>(m, pl, it, rows_for_compute, bias_for_compute, pos_of_slot,
-                                                                                     static_cast<float*>(B.grads_req.p), static_cast<float*>(B.bgrads_req.p),
-                                                                                     static_cast<float*>(B.dalpha.p), world == 1 ? send_row : nullptr));
-            ++*launches;
-            // 5. gradients to owners, sparse visits on the owner's shard
-            const float* g_own = static_cast<const float*>(B.grads_req.p); const float* bg_own = static_cast<const float*>(B.bgrads_req.p);
-            if (world > 1) {
-                SNC(exchange(B.grads_req.p, scnt, soff, B.grads_own.p, rcnt, roff, (size_t)D * 4));
-                SNC(exchange(B.bgrads_req.p, scnt, soff, B.bgrads_own.p, rcnt, roff, 4));
-                g_own = static_cast<const float*>(B.grads_own.p); bg_own = static_cast<const float*>(B.bgrads_own.p);
+            // the NEXT round's requests go to the other set, whose last readers were the kernels of the previous round
+            if (it + 1 < n_rounds) if (int rc = stage_requests(B.rs[cur ^ 1], it + 1, rounds_done + 1, it > 0 ? B.ev_round : nullptr)) return rc;
+            // 2. rows + biases back to the requesters; fused forward / backward
+            for (int q = 0; q < NGRP; ++q) {
+                GrpBufs& g = B.grp[q];
+                if (world > 1) SNC(exchange(gst[q], g.rows_own.p, rcnt[q], roff[q], g.rows_req.p, scnt[q], soff[q], (size_t)D * 4, g.bias_own.p, g.bias_req.p, 4, true));
+                mark("rows exchanged", q, gst[q], tron && world > 1);
+                const uint32_t p_lo = q ? p_split : 0, p_hi = (q || NGRP == 1) ? pl.P : p_split;
+                const int grid_p = (int)((p_hi - p_lo + 7) / 8);
+                uint2* warp_pairs = (world == 1 && m.loss == 2) ? static_cast<uint2*>(R.send_pair.p) : nullptr;
+                if (grid_p) {
+                    SYNC_DISPATCH_D(D, sync_ewma_compute_kernel<kD><<<grid_p, 256, 0, gst[q]>>>(m, pl, it, static_cast<float*>(g.rows_req.p), static_cast<float*>(g.bias_req.p),
+                                                                                             pos_of_slot, static_cast<float*>(g.grads_req.p), static_cast<float*>(g.bgrads_req.p),
+                                                                                             static_cast<float*>(B.dalpha.p), warp_pairs, p_lo, p_hi, rounds_done));
+                    ++*launches;
+                }
+                SCU(cudaEventRecord(g.ev_compute, gst[q]));
+                mark("computed", q, gst[q], tron);
             }
+            // 3. gradient rows to the owners; sparse visits on the owner's shard, group A's entries before group B's
             const uint64_t t_adam = num_updates + (rounds_done + 1) * (uint64_t)pl.P * world;
             if (o.adam) { o.c1 = 1.0f - powf(0.9f, (float)t_adam); o.c2 = 1.0f - powf(0.999f, (float)t_adam); }
-            if (nown) {
-                unsigned long long* k_in = static_cast<unsigned long long*>(B.keys_in.p); unsigned long long* k_out = static_cast<unsigned long long*>(B.keys_out.p);
-                uint32_t* v_in = static_cast<uint32_t*>(B.vals_in.p); uint32_t* v_out = static_cast<uint32_t*>(B.vals_out.p);
-                sync_keys_kernel<<<148 * 4, 256, 0, st>>>(own_rows, own_ords, nown, k_in, v_in);
-                size_t tmp = B.cub_tmp.cap;
-                SCU(cub::DeviceRadixSort::SortPairs(B.cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (int)nown, 0, 64, st));
-                SYNC_DISPATCH_D(D, sync_apply_kernel<kD><<<148 * 8, 256, 0, st>>>(m, rank, k_out, v_out, g_own, bg_own, nown, o));
-                *launches += 3;
+            for (int q = 0; q < NGRP; ++q) {
+                GrpBufs& g = B.grp[q];
+                const float* g_own = static_cast<const float*>(g.grads_req.p); const float* bg_own = static_cast<const float*>(g.bgrads_req.p);
+                if (world > 1) {
+                    SNC(exchange(gst[q], g.grads_req.p, scnt[q], soff[q], g.grads_own.p, rcnt[q], roff[q], (size_t)D * 4, g.bgrads_req.p, g.bgrads_own.p, 4, true));
+                    g_own = static_cast<const float*>(g.grads_own.p); bg_own = static_cast<const float*>(g.bgrads_own.p);
+                    mark("grads exchanged", q, gst[q], tron);
+                }
+                if (q == 0 && NGRP == 2) SCU(cudaStreamWaitEvent(gst[0], B.grp[1].ev_gather, 0));   // nobody still reads the table
+                if (q == 1) SCU(cudaStreamWaitEvent(gst[1], B.grp[0].ev_apply, 0));
+                if (nown[q]) {
+                    unsigned long long* k_in = static_cast<unsigned long long*>(g.keys_in.p); unsigned long long* k_out = static_cast<unsigned long long*>(g.keys_out.p);
+                    uint32_t* v_in = static_cast<uint32_t*>(g.vals_in.p); uint32_t* v_out = static_cast<uint32_t*>(g.vals_out.p);
+                    sync_keys_kernel<<<148 * 4, 256, 0, gst[q]>>>(own_pairs[q], nown[q], k_in, v_in);
+                    size_t tmp = g.cub_tmp.cap;
+                    SCU(cub::DeviceRadixSort::SortPairs(g.cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (int)nown[q], 0, 64, gst[q]));
+                    SelfSeg ss_g; ss_g.lo = roff[q][rank]; ss_g.n = rcnt[q][rank];
+                    ss_g.rows = static_cast<float*>(g.grads_req.p) + soff[q][rank] * D; ss_g.bias = static_cast<float*>(g.bgrads_req.p) + soff[q][rank];
+                    SYNC_DISPATCH_D(D, sync_apply_kernel<kD><<<148 * 8, 256, 0, gst[q]>>>(m, rank, k_out, v_out, g_own, bg_own, nown[q], o, ss_g));
+                    *launches += 3;
+                }
+                SCU(cudaEventRecord(g.ev_apply, gst[q]));
+                mark("applied", q, gst[q], tron);
             }
-            // 6. dense parameters: gradient summed over every partition of every rank, one step on each replica
-            if (world > 1) SNC(NC->AllReduce(B.dalpha.p, B.dalpha.p, m.ndense, ncclFloat, ncclSum, comm, st));
-            sync_dense_kernel<<<(unsigned)((m.ndense + 127) / 128), 128, 0, st>>>(m, static_cast<float*>(B.dalpha.p), o);
+            // 4. dense parameters: gradient summed over every partition of every rank, one step on each replica
+            cudaStream_t sl = gst[NGRP - 1];
+            if (NGRP == 2) SCU(cudaStreamWaitEvent(sl, B.grp[0].ev_compute, 0));
+            if (world > 1) SNC(NC->AllReduce(B.dalpha.p, B.dalpha.p, m.ndense, ncclFloat, ncclSum, comm, sl));
+            sync_dense_kernel<<<(unsigned)((m.ndense + 127) / 128), 128, 0, sl>>>(m, static_cast<float*>(B.dalpha.p), o);
             ++*launches;
+            SCU(cudaEventRecord(B.ev_round, sl));
+            mark("round done", 2, sl, tron);
+            cur ^= 1;
         }
+        if (NGRP == 2) SCU(cudaStreamWaitEvent(st, B.ev_round, 0));   // the next epoch's shuffle / the caller see a finished epoch
+    }
+    sync_advance_steps_kernel<<<(pl.P + 127) / 128, 128, 0, st>>>(pl, rounds_done);
+    ++*launches;
+    if (!tr.empty()) {
+        cudaDeviceSynchronize();
+        for (auto& pr : tr) { float ms = 0.f; cudaEventElapsedTime(&ms, tr[0].second, pr.second); fprintf(stderr, "[sync trace rank %d] %-18s %8.3f ms\n", rank, pr.first.c_str(), ms); }
+        for (auto& pr : tr) cudaEventDestroy(pr.second);
     }
     SCU(cudaGetLastError());
     return 0;

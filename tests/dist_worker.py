@@ -125,6 +125,25 @@ def main():
     uid = [pkg.dist_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     pkg.dist_init(rank, world, uid[0])
+    # ---- replicas: sbr_model_replica_sync = start + the SUM of all ranks' deltas, parameters and optimizer state, on device ----
+    rm = (pkg.lstm.Hyperparameters(N, T).embedding_dim(D).optimizer(pkg.Optimizer.Adagrad).parallelism(pkg.Parallelism.Asynchronous)
+          .num_threads(8).from_seed(seed).build())
+    assert rm.replica_sync() == 0                                  # first call: records the common starting point
+    start = {n: rm.get_parameter(n) for n in ("item_embeddings", "item_biases", "lstm_weights", "lstm_biases", "item_embeddings.s1")}
+    for n, v in start.items():                                      # this rank's "training": a rank-dependent change of every blob
+        rm.set_parameter(n, v + np.float32(0.25 * (rank + 1)) * np.sign(v + 1e-3).astype(np.float32))
+    nbytes = rm.replica_sync()
+    assert nbytes == 4 * (N * (4 + 2 * D) + 3 * (2 * D * 4 * D + 4 * D)), nbytes
+    tot = np.float32(sum(0.25 * (r + 1) for r in range(world)))
+    for n, v in start.items():
+        want = v + tot * np.sign(v + 1e-3).astype(np.float32)
+        assert np.allclose(rm.get_parameter(n), want, atol=1e-5), n
+    assert rm.replica_sync() == nbytes                              # nothing changed since: the replicas stay put
+    for n, v in start.items():
+        assert np.allclose(rm.get_parameter(n), v + tot * np.sign(v + 1e-3).astype(np.float32), atol=1e-5), n
+    if rank == 0:
+        print("dist_worker replica sync OK world=%d bytes=%d" % (world, nbytes))
+    del rm
     Nbig = 300_001
     ids_big = np.random.default_rng(3).integers(1, Nbig, size=int(ptr[-1])).astype(np.uint64)
     my_ptr2, my_ids2 = split_users(ptr, ids_big, rank, world)

@@ -20,4 +20,4 @@ def test_two_gpu_shared_model(pkg):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "dist_worker ewma OK" in out.stdout and "dist_worker lstm OK" in out.stdout
-    assert "dist_worker sync OK" in out.stdout
+    assert "dist_worker sync OK" in out.stdout and "dist_worker replica sync OK" in out.stdout
