@@ -98,8 +98,11 @@ def sharded_c4_leg(pkg, torch, dist, rank, world, steps, warmup, barrier, max_ov
            "seqs_per_gpu_per_step": int(st["steps"]), "partitions_per_gpu": int(st["partitions"]), "rounds_per_step": rounds,
            "kernel": st["kernel"], "gpu_launches_per_step": int(st["kernel_launches"]),
            "per_gpu_hbm_frac": a_bytes * ts / (kms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_timestep": a_bytes,
-           "exchange": "NCCL grouped send/recv all-to-all of (row, order) pairs, rows + biases, gradient rows; two half-round pipelines overlap "
-                       "transfers with the gather / compute / apply kernels" if world > 1 else "none (one GPU owns every row)"}
+           "exchange": ("none (one GPU owns every row)" if world == 1 else
+                        "(row, order) pairs: NCCL grouped send/recv all-to-all; rows + biases and gradient rows: plain stores of the owners' gather kernel / the "
+                        "requesters' compute kernel into peer buffers over NVLink (CUDA IPC mappings), one 4-byte all-reduce per phase as the barrier; two "
+                        "half-round pipelines on two streams" if "p2p" in st["kernel"] else
+                        "NCCL grouped send/recv all-to-all of (row, order) pairs, rows + biases, gradient rows; two half-round pipelines on two streams")}
     del plan, model
     return out
 

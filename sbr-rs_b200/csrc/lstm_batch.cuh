@@ -600,7 +600,7 @@ int run_batch_lstm(const ModelDev& m, PlanDev& pl, BatchBuffers& B, uint64_t num
             SCU(cub::DeviceRadixSort::SortPairs(B.cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (int)nslots, 0, 64, st));
             const uint64_t t_adam = num_updates + (rounds_done + 1) * (uint64_t)pl.P;
             if (o.adam) { o.c1 = 1.0f - powf(0.9f, (float)t_adam); o.c2 = 1.0f - powf(0.999f, (float)t_adam); }
-            SYNC_DISPATCH_D(D, sync_apply_kernel<kD><<<148 * 8, 256, 0, st>>>(m, 0, k_out, v_out, bp.grads, bp.bgrads, nslots, o, SelfSeg{0, 0, nullptr, nullptr}));
+            SYNC_DISPATCH_D(D, sync_apply_kernel<kD><<<148 * 8, 256, 0, st>>>(m, 0, k_out, v_out, bp.grads, bp.bgrads, nslots, o));
             sync_dense_kernel<<<(unsigned)((m.ndense + 127) / 128), 128, 0, st>>>(m, bp.dWsum, o);
             bl_finish_kernel<<<(bd.P + 127) / 128, 128, 0, st>>>(pl, bd, bp);
             *launches += 6;

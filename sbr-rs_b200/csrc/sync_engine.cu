@@ -120,21 +120,31 @@ __global__ void sync_bucket_kernel(ModelDev m, const uint32_t* __restrict__ req_
 }
 
 // owner side: copy the requested rows (weights only) and biases out of the local shard, warp per request
-// Requests that came from this rank itself (entries [self_lo, self_lo + self_n) of the owner-side list) are written straight
-// into the requester-side buffers: they never travel through NCCL.
-struct SelfSeg { size_t lo, n; float* rows; float* bias; };
+// Where entry j of a list that is segmented by peer GPU goes: segment g = [lo[g], lo[g + 1]) lands in rows[g] / bias[g] (peer
+// g's buffer, mapped through CUDA IPC -- a plain store over NVLink -- or a local one) at element base[g] + (j - lo[g]).
+struct Route {
+    int G;
+    size_t lo[9], base[8];
+    float* rows[8]; float* bias[8];
+    __device__ __forceinline__ void find(size_t j, int& g, size_t& idx) const {
+        g = 0;
+#pragma unroll
+        for (int q = 1; q < 8; ++q) if (q < G && j >= lo[q]) g = q;
+        idx = base[g] + (j - lo[g]);
+    }
+};
 template <int D>
-__global__ void __launch_bounds__(256) sync_gather_kernel(ModelDev m, int self, const uint2* __restrict__ pairs, size_t n,
-                                                          float* __restrict__ out_rows, float* __restrict__ out_bias, SelfSeg ss) {
+__global__ void __launch_bounds__(256) sync_gather_kernel(ModelDev m, int self, const uint2* __restrict__ pairs, size_t n, Route rt) {
     constexpr int V = VecOf<D>::V;
     const int lane = threadIdx.x & 31;
     for (size_t j = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n; j += (size_t)gridDim.x * (blockDim.x >> 5)) {
         const uint32_t r = pairs[j].x;
         float w[V];
         row_load_cg<D>(shard_item_rec(m, self, r), lane, w);
-        const bool mine = j >= ss.lo && j < ss.lo + ss.n;
-        vec_store<D>(mine ? ss.rows + (j - ss.lo) * D : out_rows + j * D, lane, w);
-        if (lane == 0) *(mine ? ss.bias + (j - ss.lo) : out_bias + j) = __ldcg(reinterpret_cast<const float*>(shard_bias_rec(m, self, r)));
+        int g; size_t idx;
+        rt.find(j, g, idx);
+        vec_store<D>(rt.rows[g] + idx * D, lane, w);
+        if (lane == 0) rt.bias[g][idx] = __ldcg(reinterpret_cast<const float*>(shard_bias_rec(m, self, r)));
     }
 }
 
@@ -142,8 +152,7 @@ __global__ void __launch_bounds__(256) sync_gather_kernel(ModelDev m, int self, 
 template <int D>
 __global__ void __launch_bounds__(256) sync_ewma_compute_kernel(ModelDev m, PlanDev pl, uint32_t it, float* __restrict__ rows,
                                                                 float* __restrict__ biases, const uint32_t* __restrict__ pos_of_slot,
-                                                                float* __restrict__ grads, float* __restrict__ bgrads,
-                                                                float* __restrict__ dalpha_sum, uint2* __restrict__ own_pairs,
+                                                                Route gr, float* __restrict__ dalpha_sum, uint2* __restrict__ own_pairs,
                                                                 uint32_t p_lo, uint32_t p_hi, uint64_t step_base) {
     constexpr int V = VecOf<D>::V;
     const int lane = threadIdx.x & 31;
@@ -217,10 +226,13 @@ __global__ void __launch_bounds__(256) sync_ewma_compute_kernel(ModelDev m, Plan
         }
 #pragma unroll
         for (int v = 0; v < V; ++v) { gn[v] = g * st[v]; gp[v] = -g * st[v]; }
-        vec_store<D>(grads + (size_t)pq * D, lane, gn);
-        vec_store<D>(grads + (size_t)pp * D, lane, gp);
-        vec_store<D>(grads + (size_t)px * D, lane, dx);
-        if (lane == 0) { bgrads[pq] = g; bgrads[pp] = -g; bgrads[px] = __int_as_float(0x7fc00000); }  // NaN: no bias entry for inputs
+        // the three entries go where their rows live: the owner's gradient buffer (peer memory over NVLink, or local)
+        int gq, gp_, gx; size_t iq, ip, ix;
+        gr.find(pq, gq, iq); gr.find(pp, gp_, ip); gr.find(px, gx, ix);
+        vec_store<D>(gr.rows[gq] + iq * D, lane, gn);
+        vec_store<D>(gr.rows[gp_] + ip * D, lane, gp);
+        vec_store<D>(gr.rows[gx] + ix * D, lane, dx);
+        if (lane == 0) { gr.bias[gq][iq] = g; gr.bias[gp_][ip] = -g; gr.bias[gx][ix] = __int_as_float(0x7fc00000); }  // NaN: no bias entry for inputs
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -247,7 +259,7 @@ __global__ void sync_keys_kernel(const uint2* __restrict__ pairs, size_t n, unsi
 template <int D>
 __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, const unsigned long long* __restrict__ keys,
                                                          const uint32_t* __restrict__ vals, const float* __restrict__ grads,
-                                                         const float* __restrict__ bgrads, size_t n, OptCfg o, SelfSeg ss) {
+                                                         const float* __restrict__ bgrads, size_t n, OptCfg o) {
     constexpr int V = VecOf<D>::V;
     const int lane = threadIdx.x & 31;
     const size_t stride = (size_t)gridDim.x * (blockDim.x >> 5);
@@ -259,11 +271,8 @@ __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, c
             const uint32_t rn = (uint32_t)(kn >> 32);
             if (rn != kInvalid) {
                 if (lane < rec_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(shard_bias_rec(m, self, rn)) + lane * 128));
-                else if (lane < rec_lines + grad_lines) {
-                    const size_t sn = vals[j + stride];
-                    const float* gp = (sn >= ss.lo && sn < ss.lo + ss.n) ? ss.rows + (sn - ss.lo) * D : grads + sn * D;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(gp) + (lane - rec_lines) * 128));
-                }
+                else if (lane < rec_lines + grad_lines)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(grads + (size_t)vals[j + stride] * D) + (lane - rec_lines) * 128));
             }
         }
         const uint32_t r = (uint32_t)(keys[j] >> 32);
@@ -281,9 +290,8 @@ __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, c
         if (lane == 0) bq = __ldcg(shard_bias_rec(m, self, r));
         for (size_t e = j; e < n && (uint32_t)(keys[e] >> 32) == r; ++e) {
             const size_t src = vals[e];
-            const bool mine = src >= ss.lo && src < ss.lo + ss.n;   // entries of this rank's own partitions: still in the requester-side buffers
             float g[V];
-            vec_load<D>(mine ? ss.rows + (src - ss.lo) * D : grads + src * D, lane, g);
+            vec_load<D>(grads + src * D, lane, g);
             if (!o.adam) {
 #pragma unroll
                 for (int v = 0; v < V; ++v) adagrad_elem(w[v], s1[v], g[v], o.lr, o.l2);
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, c
                 for (int v = 0; v < V; ++v) adam_elem(w[v], s1[v], s2[v], g[v], o);
             }
             if (lane == 0) {
-                const float bg = mine ? ss.bias[src - ss.lo] : bgrads[src];
+                const float bg = bgrads[src];
                 if (bg == bg) {
                     if (!o.adam) adagrad_elem(bq.x, bq.y, bg, o.lr, o.l2); else adam_elem(bq.x, bq.y, bq.z, bg, o);
                     bias_dirty = true;
@@ -362,7 +370,13 @@ struct SyncBuffers {
     unsigned int* h_scal = nullptr;     // pinned scalar for the round-count agreement
     cudaStream_t s_b = nullptr, s_req = nullptr;
     cudaEvent_t ev_round = nullptr, ev_consumed = nullptr;
+    // peer mappings (CUDA IPC) of every rank's receive buffers: [group][0 rows_req, 1 bias_req, 2 grads_own, 3 bgrads_own][rank]
+    bool p2p = false, p2p_tried = false;
+    float* peer[2][4][8] = {};
+    std::vector<void*> ipc_opened;
+    Buf ipc_dev;
     ~SyncBuffers() {
+        for (void* q : ipc_opened) cudaIpcCloseMemHandle(q);
         if (h_scal) cudaFreeHost(h_scal);
         if (s_b) cudaStreamDestroy(s_b);
         if (s_req) cudaStreamDestroy(s_req);
@@ -371,6 +385,7 @@ struct SyncBuffers {
 };
 
 SyncBuffers* sync_buffers_new() { return new SyncBuffers(); }
+bool sync_buffers_p2p(const SyncBuffers* b) { return b && b->p2p; }
 void sync_buffers_free(SyncBuffers* b) { delete b; }
 
 #define SCU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { *err = std::string(#expr) + ": " + cudaGetErrorString(e__); return 1; } } while (0)
@@ -422,9 +437,11 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
     }
     // Rows other ranks may request from this shard per round and group.  The usual load is ~ the group's own slot count; a
     // skewed id distribution (popular ids in one residue class mod world) can send up to world x that to one owner, so the
-    // owner-side buffers GROW when a round needs more (both pipelines are drained first).
+    // owner-side buffers GROW when a round needs more (both pipelines are drained first) -- except when peers hold mappings
+    // of them (p2p mode), where they are sized at twice the expected load once and a round that needs more is an error.
     auto ensure_own = [&](GrpBufs& g, size_t need) -> int {
         if (need <= g.cap_own) return 0;
+        if (B.p2p) { *err = "synchronous exchange: one owner was asked for more rows than its peer-mapped buffers hold (id distribution too skewed for id % world sharding)"; return 3; }
         SCU(cudaDeviceSynchronize());
         g.cap_own = need;
         SCU(g.keys_in.ensure(need * 8)); SCU(g.keys_out.ensure(need * 8)); SCU(g.vals_in.ensure(need * 4)); SCU(g.vals_out.ensure(need * 4));
@@ -432,19 +449,60 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
         SCU(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<unsigned long long*>(nullptr), static_cast<unsigned long long*>(nullptr),
                                             static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), (int)need, 0, 64, st));
         SCU(g.cub_tmp.ensure(cub_bytes));
-        if (world > 1) {
-            SCU(g.recv_pair.ensure(need * 8)); SCU(g.rows_own.ensure(need * D * 4)); SCU(g.bias_own.ensure(need * 4));
-            SCU(g.grads_own.ensure(need * D * 4)); SCU(g.bgrads_own.ensure(need * 4));
-        }
+        if (world > 1) { SCU(g.recv_pair.ensure(need * 8)); SCU(g.grads_own.ensure(need * D * 4)); SCU(g.bgrads_own.ensure(need * 4)); }
         return 0;
     };
     for (int q = 0; q < NGRP; ++q) {
         GrpBufs& g = B.grp[q];
         SCU(g.rows_req.ensure(slots_grp[q] * D * 4)); SCU(g.bias_req.ensure(slots_grp[q] * 4));
-        SCU(g.grads_req.ensure(slots_grp[q] * D * 4)); SCU(g.bgrads_req.ensure(slots_grp[q] * 4));
-        if (int rc = ensure_own(g, world == 1 ? slots_grp[q] : slots_grp[q] * 3 / 2 + 4096)) return rc;
+        if (world == 1) { SCU(g.grads_req.ensure(slots_grp[q] * D * 4)); SCU(g.bgrads_req.ensure(slots_grp[q] * 4)); }
+        if (int rc = ensure_own(g, world == 1 ? slots_grp[q] : slots_grp[q] * 2 + 4096)) return rc;
         for (cudaEvent_t* e : {&g.ev_gather, &g.ev_compute, &g.ev_apply}) if (!*e) SCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
+    // ---- peer mappings of the receive buffers (once per plan): rows and gradient rows then cross NVLink as plain stores of the
+    // gather / compute kernels, no staging copy and no collective on the data path.  Falls back to NCCL send/recv when any
+    // rank cannot map a peer (SBR_SYNC_NO_P2P=1 forces the fallback).
+    if (world > 1 && !B.p2p_tried) {
+        B.p2p_tried = true;
+        struct Pack { cudaIpcMemHandle_t h[2][4]; };
+        static_assert(sizeof(Pack) == 512, "8 IPC handles");
+        Pack mine{};
+        int ok = getenv("SBR_SYNC_NO_P2P") ? 0 : 1;
+        for (int q = 0; q < NGRP && ok; ++q) {
+            void* bufs[4] = {B.grp[q].rows_req.p, B.grp[q].bias_req.p, B.grp[q].grads_own.p, B.grp[q].bgrads_own.p};
+            for (int k = 0; k < 4 && ok; ++k) if (cudaIpcGetMemHandle(&mine.h[q][k], bufs[k]) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        }
+        SCU(B.ipc_dev.ensure((size_t)world * sizeof(Pack) + 64));
+        std::vector<Pack> all(world);
+        SCU(cudaMemcpyAsync(static_cast<char*>(B.ipc_dev.p) + (size_t)rank * sizeof(Pack), &mine, sizeof(Pack), cudaMemcpyHostToDevice, st));
+        SNC(NC->AllGather(static_cast<char*>(B.ipc_dev.p) + (size_t)rank * sizeof(Pack), B.ipc_dev.p, sizeof(Pack), ncclChar, comm, st));
+        SCU(cudaMemcpyAsync(all.data(), B.ipc_dev.p, (size_t)world * sizeof(Pack), cudaMemcpyDeviceToHost, st));
+        SCU(cudaStreamSynchronize(st));
+        for (int q = 0; q < NGRP && ok; ++q) {
+            void* bufs[4] = {B.grp[q].rows_req.p, B.grp[q].bias_req.p, B.grp[q].grads_own.p, B.grp[q].bgrads_own.p};
+            for (int k = 0; k < 4 && ok; ++k)
+                for (int g = 0; g < world && ok; ++g) {
+                    if (g == rank) { B.peer[q][k][g] = static_cast<float*>(bufs[k]); continue; }
+                    void* ptr = nullptr;
+                    if (cudaIpcOpenMemHandle(&ptr, all[g].h[q][k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+                    B.ipc_opened.push_back(ptr);
+                    B.peer[q][k][g] = static_cast<float*>(ptr);
+                }
+        }
+        // everybody or nobody
+        int* d_ok = reinterpret_cast<int*>(static_cast<char*>(B.ipc_dev.p) + (size_t)world * sizeof(Pack));
+        SCU(cudaMemcpyAsync(d_ok, &ok, 4, cudaMemcpyHostToDevice, st));
+        SNC(NC->AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, st));
+        SCU(cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, st));
+        SCU(cudaStreamSynchronize(st));
+        B.p2p = ok != 0;
+    }
+    if (world > 1 && !B.p2p)   // NCCL fallback: staging buffers on both sides
+        for (int q = 0; q < NGRP; ++q) {
+            GrpBufs& g = B.grp[q];
+            SCU(g.rows_own.ensure(g.cap_own * D * 4)); SCU(g.bias_own.ensure(g.cap_own * 4));
+            SCU(g.grads_req.ensure(slots_grp[q] * D * 4)); SCU(g.bgrads_req.ensure(slots_grp[q] * 4));
+        }
     SCU(cudaMemsetAsync(B.dalpha.p, 0, m.ndense * 4, st));
     OptCfg o; o.lr = m.lr; o.l2 = m.l2; o.adam = m.opt == 1; o.c1 = 1.0f; o.c2 = 1.0f;
     cudaStream_t gst[2] = {st, B.s_b};
@@ -523,6 +581,12 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
                     rcnt[q][g] = world > 1 ? R.h_counts[g * 16 + q * G + rank] : scnt[q][g]; roff[q][g] = ro; ro += rcnt[q][g];
                 }
                 nown[q] = ro;
+                if (B.p2p)   // peer-mapped buffers cannot grow: every rank sees every rank's load, so all ranks give up together
+                    for (int g = 0; g < G; ++g) {
+                        size_t load = 0;
+                        for (int src = 0; src < G; ++src) load += R.h_counts[src * 16 + q * G + g];
+                        if (load > B.grp[q].cap_own) { *err = "synchronous exchange: one owner was asked for more rows than its peer-mapped buffers hold (id distribution too skewed for id % world sharding)"; return 3; }
+                    }
                 if (int rc = ensure_own(B.grp[q], nown[q])) return rc;
             }
             // both pipelines start once the previous round's table is final and the epoch shuffle (stream `st`) has run
@@ -543,12 +607,21 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
                     own_pairs[q] = static_cast<const uint2*>(g.recv_pair.p);
                     mark("pairs exchanged", q, gst[q], tron);
                 }
-                float* own_rows_buf = static_cast<float*>(world > 1 ? g.rows_own.p : g.rows_req.p);
-                float* own_bias_buf = static_cast<float*>(world > 1 ? g.bias_own.p : g.bias_req.p);
-                // this rank's own requests (owner-side entries [roff[rank], + rcnt[rank])  ==  requester-side entries [soff[rank], ..))
-                SelfSeg ss_rows; ss_rows.lo = roff[q][rank]; ss_rows.n = rcnt[q][rank];
-                ss_rows.rows = static_cast<float*>(g.rows_req.p) + soff[q][rank] * D; ss_rows.bias = static_cast<float*>(g.bias_req.p) + soff[q][rank];
-                if (nown[q]) { SYNC_DISPATCH_D(D, sync_gather_kernel<kD><<<148 * 8, 256, 0, gst[q]>>>(m, rank, own_pairs[q], nown[q], own_rows_buf, own_bias_buf, ss_rows)); ++*launches; }
+                // where the gathered rows go: segment g of the owner-side list came from rank g and belongs at that rank's
+                // requester-side position soff_g[me] + i -- in its rows_req buffer (p2p: a store over NVLink; own segment: local;
+                // NCCL fallback: the local staging buffer, identity position)
+                Route rt; rt.G = G;
+                for (int g2 = 0; g2 < G; ++g2) {
+                    rt.lo[g2] = roff[q][g2];
+                    size_t soff_at = 0;   // position of my segment in rank g2's send list of this group
+                    for (int o2 = 0; o2 < rank; ++o2) soff_at += world > 1 ? R.h_counts[g2 * 16 + q * G + o2] : 0;
+                    const bool direct = B.p2p || g2 == rank || world == 1;
+                    rt.base[g2] = direct ? soff_at : roff[q][g2];
+                    rt.rows[g2] = direct ? (world > 1 ? (B.p2p ? B.peer[q][0][g2] : static_cast<float*>(g.rows_req.p)) : static_cast<float*>(g.rows_req.p)) : static_cast<float*>(g.rows_own.p);
+                    rt.bias[g2] = direct ? (world > 1 ? (B.p2p ? B.peer[q][1][g2] : static_cast<float*>(g.bias_req.p)) : static_cast<float*>(g.bias_req.p)) : static_cast<float*>(g.bias_own.p);
+                }
+                for (int g2 = G; g2 <= 8; ++g2) rt.lo[g2] = nown[q];
+                if (nown[q]) { SYNC_DISPATCH_D(D, sync_gather_kernel<kD><<<148 * 8, 256, 0, gst[q]>>>(m, rank, own_pairs[q], nown[q], rt)); ++*launches; }
                 SCU(cudaEventRecord(g.ev_gather, gst[q]));
                 mark("gathered", q, gst[q], tron);
             }
@@ -557,15 +630,29 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
             // 2. rows + biases back to the requesters; fused forward / backward
             for (int q = 0; q < NGRP; ++q) {
                 GrpBufs& g = B.grp[q];
-                if (world > 1) SNC(exchange(gst[q], g.rows_own.p, rcnt[q], roff[q], g.rows_req.p, scnt[q], soff[q], (size_t)D * 4, g.bias_own.p, g.bias_req.p, 4, true));
+                if (world > 1 && !B.p2p) SNC(exchange(gst[q], g.rows_own.p, rcnt[q], roff[q], g.rows_req.p, scnt[q], soff[q], (size_t)D * 4, g.bias_own.p, g.bias_req.p, 4, true));
+                if (B.p2p) SNC(NC->AllReduce(static_cast<int*>(B.scal.p) + 4 + q, static_cast<int*>(B.scal.p) + 4 + q, 1, ncclInt, ncclSum, comm, gst[q]));   // every rank's rows have landed
                 mark("rows exchanged", q, gst[q], tron && world > 1);
                 const uint32_t p_lo = q ? p_split : 0, p_hi = (q || NGRP == 1) ? pl.P : p_split;
                 const int grid_p = (int)((p_hi - p_lo + 7) / 8);
                 uint2* warp_pairs = (world == 1 && m.loss == 2) ? static_cast<uint2*>(R.send_pair.p) : nullptr;
+                // where the gradient entries go: requester-side position pos in segment g belongs at owner g's list position
+                // roff_g[me] + i -- in its grads_own buffer (p2p / own segment) or in the local staging buffer (NCCL fallback)
+                Route gr; gr.G = G;
+                size_t sent = 0;
+                for (int g2 = 0; g2 < G; ++g2) {
+                    gr.lo[g2] = soff[q][g2]; sent = soff[q][g2] + scnt[q][g2];
+                    size_t roff_at = 0;   // where my entries start in rank g2's owner-side list of this group
+                    for (int s2 = 0; s2 < rank; ++s2) roff_at += world > 1 ? R.h_counts[s2 * 16 + q * G + g2] : 0;
+                    const bool direct = B.p2p || (g2 == rank && world > 1);
+                    gr.base[g2] = direct ? roff_at : soff[q][g2];
+                    gr.rows[g2] = direct ? (B.p2p ? B.peer[q][2][g2] : static_cast<float*>(g.grads_own.p)) : static_cast<float*>(g.grads_req.p);
+                    gr.bias[g2] = direct ? (B.p2p ? B.peer[q][3][g2] : static_cast<float*>(g.bgrads_own.p)) : static_cast<float*>(g.bgrads_req.p);
+                }
+                for (int g2 = G; g2 <= 8; ++g2) gr.lo[g2] = sent;
                 if (grid_p) {
                     SYNC_DISPATCH_D(D, sync_ewma_compute_kernel<kD><<<grid_p, 256, 0, gst[q]>>>(m, pl, it, static_cast<float*>(g.rows_req.p), static_cast<float*>(g.bias_req.p),
-                                                                                             pos_of_slot, static_cast<float*>(g.grads_req.p), static_cast<float*>(g.bgrads_req.p),
-                                                                                             static_cast<float*>(B.dalpha.p), warp_pairs, p_lo, p_hi, rounds_done));
+                                                                                             pos_of_slot, gr, static_cast<float*>(B.dalpha.p), warp_pairs, p_lo, p_hi, rounds_done));
                     ++*launches;
                 }
                 SCU(cudaEventRecord(g.ev_compute, gst[q]));
@@ -576,10 +663,11 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
             if (o.adam) { o.c1 = 1.0f - powf(0.9f, (float)t_adam); o.c2 = 1.0f - powf(0.999f, (float)t_adam); }
             for (int q = 0; q < NGRP; ++q) {
                 GrpBufs& g = B.grp[q];
-                const float* g_own = static_cast<const float*>(g.grads_req.p); const float* bg_own = static_cast<const float*>(g.bgrads_req.p);
+                const float* g_own = static_cast<const float*>(world > 1 ? g.grads_own.p : g.grads_req.p);
+                const float* bg_own = static_cast<const float*>(world > 1 ? g.bgrads_own.p : g.bgrads_req.p);
                 if (world > 1) {
-                    SNC(exchange(gst[q], g.grads_req.p, scnt[q], soff[q], g.grads_own.p, rcnt[q], roff[q], (size_t)D * 4, g.bgrads_req.p, g.bgrads_own.p, 4, true));
-                    g_own = static_cast<const float*>(g.grads_own.p); bg_own = static_cast<const float*>(g.bgrads_own.p);
+                    if (!B.p2p) SNC(exchange(gst[q], g.grads_req.p, scnt[q], soff[q], g.grads_own.p, rcnt[q], roff[q], (size_t)D * 4, g.bgrads_req.p, g.bgrads_own.p, 4, true));
+                    else SNC(NC->AllReduce(static_cast<int*>(B.scal.p) + 6 + q, static_cast<int*>(B.scal.p) + 6 + q, 1, ncclInt, ncclSum, comm, gst[q]));   // every rank's entries have landed
                     mark("grads exchanged", q, gst[q], tron);
                 }
                 if (q == 0 && NGRP == 2) SCU(cudaStreamWaitEvent(gst[0], B.grp[1].ev_gather, 0));   // nobody still reads the table
@@ -590,9 +678,7 @@ int run_sync_ewma(const ModelDev& m, PlanDev& pl, SyncBuffers& B, void* comm_v, 
                     sync_keys_kernel<<<148 * 4, 256, 0, gst[q]>>>(own_pairs[q], nown[q], k_in, v_in);
                     size_t tmp = g.cub_tmp.cap;
                     SCU(cub::DeviceRadixSort::SortPairs(g.cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (int)nown[q], 0, 64, gst[q]));
-                    SelfSeg ss_g; ss_g.lo = roff[q][rank]; ss_g.n = rcnt[q][rank];
-                    ss_g.rows = static_cast<float*>(g.grads_req.p) + soff[q][rank] * D; ss_g.bias = static_cast<float*>(g.bgrads_req.p) + soff[q][rank];
-                    SYNC_DISPATCH_D(D, sync_apply_kernel<kD><<<148 * 8, 256, 0, gst[q]>>>(m, rank, k_out, v_out, g_own, bg_own, nown[q], o, ss_g));
+                    SYNC_DISPATCH_D(D, sync_apply_kernel<kD><<<148 * 8, 256, 0, gst[q]>>>(m, rank, k_out, v_out, g_own, bg_own, nown[q], o));
                     *launches += 3;
                 }
                 SCU(cudaEventRecord(g.ev_apply, gst[q]));

@@ -34,6 +34,88 @@ def split_users(ptr, ids, rank, world):
     return new_ptr, (np.concatenate(pieces) if pieces else np.zeros(0, dtype=np.uint64))
 
 
+def multi_rank_round_equals_oracle(pkg, rank, world, seed):
+    """One synchronous round over ALL ranks' partitions against the oracle, element-wise: every partition of every rank trains
+    one sequence over its own items; the round's result is: every visited row = the oracle's entries (gradients taken at the
+    initial parameters) applied un-merged in the reference order -- rank-major, then partition, then the oracle's order inside
+    a sequence -- whoever owns the row and on whichever GPU the sequence was computed; alpha = ONE Adagrad step on the
+    gradient summed over the world * P sequences."""
+    import ctypes as C
+    import oracle_lib as O
+    from test_gpu_lstm_tc import _adagrad
+    N, T, D, P, lr, l2 = 200_003, 8, 32, 8, 0.05, 1e-3
+    ptr = (np.arange(P + 1) * T).astype(np.uint64)
+    all_ids = [(1000 + 5000 * r + np.arange(P * T)).astype(np.uint64) for r in range(world)]
+    h = (pkg.ewma.Hyperparameters(N, T).embedding_dim(D).learning_rate(lr).l2_penalty(l2).loss(pkg.Loss.BPR)
+         .optimizer(pkg.Optimizer.Adagrad).parallelism(pkg.Parallelism.Synchronous).num_epochs(1).num_threads(P).from_seed(seed))
+    gm = h.shard(rank, world).build()
+    gm.ipc_attach(exchange_handles(gm, world))
+    r0 = np.random.default_rng(11)
+    E0 = (r0.standard_normal((N, D)) * 0.3).astype(np.float32)
+    b0 = (r0.standard_normal(N) * 0.3).astype(np.float32)
+    A0 = (r0.standard_normal(D) * 0.5).astype(np.float32)
+    dist.barrier()
+    gm.set_parameter("item_embeddings", E0.ravel()); gm.set_parameter("item_biases", b0)   # every rank writes its own rows
+    gm.set_parameter("alpha", A0)
+    for n_ in ("item_embeddings", "item_biases", "alpha"):
+        gm.set_parameter(n_ + ".s1", np.ones(len(gm.get_parameter(n_)), dtype=np.float32))
+    dist.barrier()
+    om = O.OracleModel("ewma", N, T, embedding_dim=D, learning_rate=lr, l2_penalty=l2, loss="bpr", optimizer="adagrad",
+                       parallelism="synchronous", num_threads=P, num_epochs=1, seed=seed)
+    om.param("item_embeddings")[:] = E0.ravel(); om.param("item_biases")[:] = b0; om.param("alpha")[:] = A0
+    for n_ in ("item_embeddings", "item_biases", "alpha"):
+        om.param(n_ + ".s1")[:] = 1.0
+    L = O.lib()
+    rng = O.Rng(*gm.rng_state)                       # the same master rng on every rank: same shuffle, same partition keys
+    order = np.arange(P, dtype=np.uint32)
+    L.sbo_shuffle_u32(C.byref(rng), order.ctypes.data_as(O.u32p), P)
+    keys = []
+    for _ in range(P):
+        sd = bytes(L.sbo_rng_next_u32(C.byref(rng)) & 0xFF for _ in range(16))
+        keys.append(int.from_bytes(sd[:8], "little"))
+    E, SE, b, Sb = E0.copy(), np.ones_like(E0), b0.copy(), np.ones_like(b0)
+    dsum = np.zeros(D, dtype=np.float32)
+    touched = {}
+    for r in range(world):                           # rank-major = the engine's application order (part_base = rank * P)
+        for p in range(P):
+            sq = int(order[p])
+            seq = all_ids[r][sq * T:(sq + 1) * T]
+            _, negs, dg = om.step(seq, key=keys[p], step=0, apply=False)
+            dsum += dg
+            rows, grads, brows, bgrads = om.last_sparse_grads()
+            for row in set(rows.tolist()) | set(brows.tolist()):
+                touched.setdefault(row, set()).add((r, p))
+            for row, gr in zip(rows.tolist(), grads):
+                E[row], SE[row] = _adagrad(E[row], SE[row], gr, lr, l2)
+            for row, gr in zip(brows.tolist(), bgrads.tolist()):
+                wv, gv = _adagrad(b[row:row + 1], Sb[row:row + 1], gr, lr, l2)
+                b[row], Sb[row] = wv[0], gv[0]
+    A1, _ = _adagrad(A0, np.ones_like(A0), dsum, lr, l2)
+    data = pkg.CompressedInteractions.from_csr(ptr, all_ids[rank], None, num_items=N)
+    dist.barrier()
+    gm.fit(data)
+    dist.barrier()
+    # (partition p draws the same negatives on every rank -- same key, same step -- so a negative's row is visited once per
+    # rank: the expected values above took those entries in the engine's order, rank-major; nothing needs to be left out)
+    clean = np.array(sorted(touched), dtype=np.int64)
+    assert sum(1 for v in touched.values() if len(v) > 1) >= P
+    gE = gm.get_parameter("item_embeddings").reshape(N, D)
+    gb = gm.get_parameter("item_biases")
+    gS = gm.get_parameter("item_embeddings.s1").reshape(N, D)
+    assert np.abs(E[clean] - E0[clean]).mean() > 1e-4
+    assert np.abs(gE[clean] - E[clean]).max() <= 2e-4, np.abs(gE[clean] - E[clean]).max()
+    assert np.abs(gb[clean] - b[clean]).max() <= 2e-4
+    assert np.abs(gS[clean] - SE[clean]).max() <= 2e-4
+    assert np.abs(gm.get_parameter("alpha") - A1).max() <= 2e-4, np.abs(gm.get_parameter("alpha") - A1).max()
+    untouched = np.setdiff1d(np.arange(N), np.array(sorted(touched), dtype=np.int64))
+    assert np.array_equal(gE[untouched], E0[untouched])
+    assert gm.last_fit_stats()["partitions"] == P
+    if rank == 0:
+        print("dist_worker sync oracle-equality OK world=%d rows=%d kernel=%s" % (world, len(clean), gm.last_fit_stats()["kernel"]))
+    dist.barrier()
+    del gm
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -172,6 +254,7 @@ def main():
     assert all(torch.equal(c, chks[0]) for c in chks)           # every rank reads the same table
     st = sm.last_fit_stats()
     assert st["kernel_launches"] > 10
+    multi_rank_round_equals_oracle(pkg, rank, world, seed)
     if rank == 0:
         print("dist_worker sync OK world=%d losses=%s launches=%d" % (world, [round(x, 4) for x in sl], st["kernel_launches"]))
     dist.barrier()

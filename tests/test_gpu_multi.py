@@ -21,3 +21,4 @@ def test_two_gpu_shared_model(pkg):
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "dist_worker ewma OK" in out.stdout and "dist_worker lstm OK" in out.stdout
     assert "dist_worker sync OK" in out.stdout and "dist_worker replica sync OK" in out.stdout
+    assert "dist_worker sync oracle-equality OK" in out.stdout
