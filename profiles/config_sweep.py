@@ -19,6 +19,7 @@ LOSS = {"warp": pkg.Loss.WARP, "hinge": pkg.Loss.Hinge, "bpr": pkg.Loss.BPR}
 OPT = {"adagrad": pkg.Optimizer.Adagrad, "adam": pkg.Optimizer.Adam}
 for name in (sys.argv[1:] or list(CONFIGS)):
     kind, N, D, L, S, loss, opt = CONFIGS[name]
+    S = int(os.environ.get("SBR_SWEEP_SEQS", S))   # (profiling runs use a smaller stream)
     rng = np.random.default_rng(42)
     ptr = np.arange(S + 1, dtype=np.uint64) * np.uint64(L)
     ids = rng.integers(1, N, size=S * L, dtype=np.uint64)

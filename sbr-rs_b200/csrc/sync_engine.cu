@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, c
         if (o.adam) row_load_cg<D>(rec + 2 * D, lane, s2);
         float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
         bool bias_dirty = false;
+        const float rc1 = 1.0f / o.c1, rc2 = 1.0f / o.c2;
         if (lane == 0) bq = __ldcg(shard_bias_rec(m, self, r));
         for (size_t e = j; e < n && (uint32_t)(keys[e] >> 32) == r; ++e) {
             const size_t src = vals[e];
@@ -296,8 +297,15 @@ __global__ void __launch_bounds__(256) sync_apply_kernel(ModelDev m, int self, c
 #pragma unroll
                 for (int v = 0; v < V; ++v) adagrad_elem(w[v], s1[v], g[v], o.lr, o.l2);
             } else {
+                // adam_elem with the two bias corrections as reciprocals (one division per entry instead of three per element;
+                // profiles/r2_c3_sync_apply_ncu_full.txt: this kernel was issue-bound on IEEE divisions, not memory-bound)
 #pragma unroll
-                for (int v = 0; v < V; ++v) adam_elem(w[v], s1[v], s2[v], g[v], o);
+                for (int v = 0; v < V; ++v) {
+                    const float gg = g[v] + w[v] * o.l2;
+                    s1[v] = 0.9f * s1[v] + (1.0f - 0.9f) * gg;
+                    s2[v] = 0.999f * s2[v] + (1.0f - 0.999f) * gg * gg;
+                    w[v] -= __fdividef(o.lr * (s1[v] * rc1), sqrtf(s2[v] * rc2) + 1e-8f);
+                }
             }
             if (lane == 0) {
                 const float bg = bgrads[src];
