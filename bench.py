@@ -99,6 +99,9 @@ def sharded_c4_leg(pkg, torch, dist, rank, world, steps, warmup, barrier, max_ov
            "kernel": st["kernel"], "gpu_launches_per_step": int(st["kernel_launches"]),
            "per_gpu_hbm_frac": a_bytes * ts / (kms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_timestep": a_bytes,
            "exchange": ("none (one GPU owns every row)" if world == 1 else
+                        "(row, order) pairs: NCCL grouped send/recv all-to-all; rows + biases and gradient rows: pushed into the peers' buffers over NVLink "
+                        "(CUDA IPC mappings) by the copy engines, one stream per peer, one 4-byte all-reduce per phase as the barrier; two half-round "
+                        "pipelines on two streams" if "copy engines" in st["kernel"] else
                         "(row, order) pairs: NCCL grouped send/recv all-to-all; rows + biases and gradient rows: plain stores of the owners' gather kernel / the "
                         "requesters' compute kernel into peer buffers over NVLink (CUDA IPC mappings), one 4-byte all-reduce per phase as the barrier; two "
                         "half-round pipelines on two streams" if "p2p" in st["kernel"] else

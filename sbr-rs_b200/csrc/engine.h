@@ -81,6 +81,7 @@ int lstm_tile_tiles_per_cta(const ModelDev& m, uint32_t P);
 struct SyncBuffers;
 SyncBuffers* sync_buffers_new();
 void sync_buffers_free(SyncBuffers* b);
+bool sync_buffers_copy_engine(const SyncBuffers* b);   // ... pushed by the copy engines from a staging buffer rather than stored by the kernels
 bool sync_buffers_p2p(const SyncBuffers* b);   // rows / gradient rows travel as peer stores (CUDA IPC mappings) instead of NCCL send/recv
 bool sync_supported(const ModelDev& m, const char** why);
 }  // namespace sbr
