@@ -110,6 +110,49 @@ def sharded_c4_leg(pkg, torch, dist, rank, world, steps, warmup, barrier, max_ov
     return out
 
 
+def wide_lstm_leg(pkg, name, rank, world, steps, barrier, max_over_ranks):
+    """BASELINE configs[2] (C3: 1 M items, LSTM dim 64 seq 64 Hinge Adam) and configs[4] (C5: ML-20M-shaped, 27 K items, LSTM dim 256
+    seq 200 WARP Adagrad): the batched round engine on tcgen05 GEMMs (lstm_batch.cuh), device-resident plan, one epoch over a
+    synthetic stream per step.  N > 1: a full replica per GPU on its own users, sbr_model_replica_sync (one ncclAllReduce of the
+    parameter / optimizer-state deltas) after every step, inside the timed region -- the "1 vs 8 scaling" of configs[4]."""
+    N, D, L, S, loss, opt, lr = {"c3": (1_000_000, 64, 64, 1 << 19, pkg.Loss.Hinge, pkg.Optimizer.Adam, 0.01),
+                                 "c5": (27_000, 256, 200, 1 << 17, pkg.Loss.WARP, pkg.Optimizer.Adagrad, 0.16)}[name]
+    rng = np.random.default_rng(5000 + rank)
+    ptr = np.arange(S + 1, dtype=np.uint64) * np.uint64(L)
+    ids = rng.integers(1, N, size=S * L, dtype=np.uint64)
+    model = (pkg.lstm.Hyperparameters(N, L).embedding_dim(D).learning_rate(lr).l2_penalty(4e-4).loss(loss).optimizer(opt)
+             .lstm_variant(pkg.LSTMVariant.Normal).parallelism(pkg.Parallelism.Asynchronous).num_epochs(1).num_threads(0)
+             .from_seed(bytes(range(16))).build())
+    plan = model.fit_plan(pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N).upload())
+    if world > 1:
+        model.replica_sync()
+    plan.run()
+    if world > 1:
+        model.replica_sync()
+    barrier()
+    t0 = time.perf_counter()
+    kms, ts = 0.0, 0
+    for _ in range(steps):
+        plan.run()
+        if world > 1:
+            model.replica_sync()
+        st = plan.stats()
+        kms += st["train_kernel_ms"]; ts += st["timesteps"]
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - t0)
+    st = plan.stats()
+    a_bytes = (84 * D + 68) if name == "c3" else (60 * D + 52)
+    out = {"value": world * st["steps"] * steps / wall, "unit": "steps/s", "ms_per_step": wall / steps * 1e3,
+           "timesteps_per_s": world * ts / wall, "gemm_tflops_algorithmic": world * ts / wall * 48 * D * D / 1e12,
+           "seqs_per_gpu_per_step": int(st["steps"]), "partitions_per_gpu": int(st["partitions"]), "kernel": st["kernel"],
+           "gpu_launches_per_step": int(st["kernel_launches"]), "per_gpu_hbm_frac": a_bytes * ts / (kms * 1e-3) / 1e9 / peaks()[0],
+           "algorithmic_bytes_per_timestep": a_bytes,
+           "workload": {"c3": "synthetic 1M items, LSTM Normal dim=64 seq=64 Hinge Adam (BASELINE configs[2])",
+                        "c5": "ML-20M-shaped 27K items, LSTM Normal dim=256 seq=200 WARP Adagrad (BASELINE configs[4])"}[name]}
+    del plan, model
+    return out
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -395,6 +438,11 @@ def main():
     if os.environ.get("SBR_BENCH_C4", "1") != "0":
         c4 = sharded_c4_leg(pkg, torch, dist, rank, world, args.steps, args.warmup, barrier, max_over_ranks)
 
+    wide = {}
+    if os.environ.get("SBR_BENCH_WIDE", "1") != "0":
+        for cname in ("c3", "c5"):
+            wide[cname] = wide_lstm_leg(pkg, cname, rank, world, max(2, min(args.steps, 3)), barrier, max_over_ranks)
+
     if rank == 0:
         peak, peak_kind = peaks()
         per_launch_bytes = A_TRAIN_BYTES_PER_TIMESTEP * (timesteps / max(launches, 1))
@@ -437,6 +485,8 @@ def main():
         }
         if c4:
             out["sharded_c4"] = c4
+        for cname, leg in wide.items():
+            out[cname] = leg
         if zipf:
             out["zipf"] = zipf
         if world == 1:
