@@ -101,7 +101,7 @@ def sharded_c4_leg(pkg, torch, dist, rank, world, steps, warmup, barrier, max_ov
            "exchange": ("none (one GPU owns every row)" if world == 1 else
                         "(row, order) pairs: NCCL grouped send/recv all-to-all; rows + biases and gradient rows: pushed into the peers' buffers over NVLink "
                         "(CUDA IPC mappings) by the copy engines, one stream per peer, one 4-byte all-reduce per phase as the barrier; two half-round "
-                        "pipelines on two streams" if "copy engines" in st["kernel"] else
+                        "pipelines on two streams" if "p2p copy" in st["kernel"] else
                         "(row, order) pairs: NCCL grouped send/recv all-to-all; rows + biases and gradient rows: plain stores of the owners' gather kernel / the "
                         "requesters' compute kernel into peer buffers over NVLink (CUDA IPC mappings), one 4-byte all-reduce per phase as the barrier; two "
                         "half-round pipelines on two streams" if "p2p" in st["kernel"] else

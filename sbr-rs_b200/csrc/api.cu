@@ -1535,7 +1535,7 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
         const int rc = run_sync_ewma(md, pl->dev, *pl->sync, g_comm, m->h.shard_rank, world, m->num_updates, st, &launches, &sync_rounds, &err);
         if (rc) return fail(rc == 2 ? SBR_ERR_NCCL : rc == 3 ? SBR_ERR_INVALID_ARGUMENT : SBR_ERR_CUDA, err);
         std::snprintf(pl->stats.kernel, sizeof(pl->stats.kernel), "sync_ewma_compute_kernel<%d> (round-synchronous%s)", m->dev.D,
-                      world == 1 ? "" : sync_buffers_copy_engine(pl->sync) ? ", p2p rows via copy engines" : sync_buffers_p2p(pl->sync) ? ", p2p rows via SM stores" : ", nccl rows");
+                      world == 1 ? "" : sync_buffers_copy_engine(pl->sync) ? ", p2p copy engines" : sync_buffers_p2p(pl->sync) ? ", p2p stores" : ", nccl");
     } else if (pl->dev.epochs > 0) {
         if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before an asynchronous fit");
         cudaError_t e;
