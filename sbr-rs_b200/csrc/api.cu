@@ -655,7 +655,7 @@ sbr_status sbr_set_device(int device) {
 
 // ------------------------------------------------------------------------------------------------ data.rs --
 sbr_status sbr_compressed_from_triplets(const uint64_t* user_ids, const uint64_t* item_ids, const uint64_t* timestamps,
-                                        size_t nnz, size_t num_users, size_t num_items, sbr_compressed** out) {
+                                        size_t nnz, size_t num_users, size_t num_items, sbr_compressed** out) try {
     if (!out || (nnz && (!user_ids || !item_ids || !timestamps))) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if (num_items > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "num_items must fit in 32 bits");
     for (size_t i = 0; i < nnz; ++i) {
@@ -683,10 +683,10 @@ sbr_status sbr_compressed_from_triplets(const uint64_t* user_ids, const uint64_t
     c->own_views();
     *out = c;
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_compressed_from_triplets: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_compressed_from_triplets: unknown C++ exception"); }
 
 sbr_status sbr_compressed_from_triplets_device(const uint64_t* user_ids, const uint64_t* item_ids, const uint64_t* timestamps,
-                                               size_t nnz, size_t num_users, size_t num_items, sbr_compressed** out) {
+                                               size_t nnz, size_t num_users, size_t num_items, sbr_compressed** out) try {
     if (!out || (nnz && (!user_ids || !item_ids || !timestamps))) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if (num_items > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "num_items must fit in 32 bits");
     sbr_status s = require_device();
@@ -708,10 +708,10 @@ sbr_status sbr_compressed_from_triplets_device(const uint64_t* user_ids, const u
     c->d_item_ids = d_ids; c->d_user_ptr = d_ptr;   // the CSR is already resident: the first fit() uploads nothing
     *out = c;
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_compressed_from_triplets_device: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_compressed_from_triplets_device: unknown C++ exception"); }
 
 sbr_status sbr_compressed_from_csr(const uint64_t* user_pointers, const uint64_t* item_ids, const uint64_t* timestamps,
-                                   size_t num_users, size_t num_items, sbr_compressed** out) {
+                                   size_t num_users, size_t num_items, sbr_compressed** out) try {
     if (!out || !user_pointers) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if (num_items > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "num_items must fit in 32 bits");
     if (user_pointers[0] != 0) return fail(SBR_ERR_INVALID_ARGUMENT, "user_pointers[0] must be 0");
@@ -729,7 +729,7 @@ sbr_status sbr_compressed_from_csr(const uint64_t* user_pointers, const uint64_t
     c->own_views();
     *out = c;
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_compressed_from_csr: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_compressed_from_csr: unknown C++ exception"); }
 
 sbr_status sbr_compressed_borrow_csr(const uint64_t* user_pointers, const uint64_t* item_ids, const uint64_t* timestamps,
                                      size_t num_users, size_t num_items, sbr_compressed** out) {
@@ -761,7 +761,7 @@ sbr_status sbr_compressed_borrow(const sbr_compressed* c, const uint64_t** user_
 }
 
 sbr_status sbr_compressed_user_chunks(const sbr_compressed* c, size_t user_id, size_t chunk_size, uint64_t* starts,
-                                      uint64_t* lens, size_t cap, size_t* n) {
+                                      uint64_t* lens, size_t cap, size_t* n) try {
     if (!c || !n) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if (user_id >= c->num_users) return fail(SBR_ERR_INVALID_ARGUMENT, "user id out of range");  // data.rs:278-280
     if (chunk_size == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "chunk_size must be > 0");
@@ -775,7 +775,7 @@ sbr_status sbr_compressed_user_chunks(const sbr_compressed* c, size_t user_id, s
     }
     *n = k;
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_compressed_user_chunks: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_compressed_user_chunks: unknown C++ exception"); }
 
 sbr_status sbr_compressed_upload(sbr_compressed* c) {
     if (!c) return fail(SBR_ERR_INVALID_ARGUMENT, "null handle");
@@ -834,7 +834,7 @@ sbr_status sbr_hyper_from_seed(sbr_hyperparameters* h, const uint8_t seed[16]) {
 }
 void sbr_hyper_free(sbr_hyperparameters* h) { delete h; }
 
-sbr_status sbr_hyper_build(sbr_hyperparameters* hp, sbr_model** out) {
+sbr_status sbr_hyper_build(sbr_hyperparameters* hp, sbr_model** out) try {
     if (!hp || !out) { delete hp; return fail(SBR_ERR_INVALID_ARGUMENT, "null argument"); }
     sbr_hyperparameters h = *hp;
     delete hp;  // build(self) consumes
@@ -887,7 +887,7 @@ sbr_status sbr_hyper_build(sbr_hyperparameters* hp, sbr_model** out) {
     if ((e = cudaStreamSynchronize(m->stream)) != cudaSuccess) return bail(e, "build sync");
     *out = m;
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_hyper_build: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_hyper_build: unknown C++ exception"); }
 
 // --------------------------------------------------------------------------------------------- multi-GPU ----
 sbr_status sbr_hyper_shard(sbr_hyperparameters* h, int rank, int world) {
@@ -960,7 +960,7 @@ extern "C" {
 // state (item records, dense weights) since the last call are summed over the ranks with one ncclAllReduce on device buffers
 // and applied to the common starting point.  The first call only records the starting point (the replicas must be identical
 // then: same seed / same checkpoint).  Needs sbr_dist_init; the model must not be row-sharded.
-sbr_status sbr_model_replica_sync(sbr_model* m, size_t* bytes_reduced) {
+sbr_status sbr_model_replica_sync(sbr_model* m, size_t* bytes_reduced) try {
     if (!m) return fail(SBR_ERR_INVALID_ARGUMENT, "null model");
     sbr_status s = require_device();
     if (s) return s;
@@ -993,7 +993,7 @@ sbr_status sbr_model_replica_sync(sbr_model* m, size_t* bytes_reduced) {
     CU(cudaStreamSynchronize(st));
     if (bytes_reduced) *bytes_reduced = n * sizeof(float);
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_model_replica_sync: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_model_replica_sync: unknown C++ exception"); }
 
 size_t sbr_model_ipc_handle_size(void) { return 2 * sizeof(cudaIpcMemHandle_t); }
 
@@ -1182,7 +1182,7 @@ std::vector<std::string> ckpt_blob_names(const sbr_hyperparameters& h) {
 struct FileCloser { FILE* f; ~FileCloser() { if (f) fclose(f); } };
 }  // namespace
 
-sbr_status sbr_model_save(const sbr_model* m, const char* path) {
+sbr_status sbr_model_save(const sbr_model* m, const char* path) try {
     if (!m || !path) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     sbr_status s = require_device();
     if (s) return s;
@@ -1219,7 +1219,7 @@ sbr_status sbr_model_save(const sbr_model* m, const char* path) {
         if (fwrite(buf.data(), 4, buf.size(), f) != buf.size()) return fail(SBR_ERR_INVALID_ARGUMENT, "short write (blob)");
     }
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_model_save: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_model_save: unknown C++ exception"); }
 
 static sbr_status ckpt_read(const char* path, sbr_hyper_values* hv, uint32_t rs[4], uint64_t* num_updates, std::vector<CkptBlob>* dir, FILE** fout) {
     FILE* f = fopen(path, "rb");
@@ -1255,7 +1255,7 @@ static sbr_status ckpt_apply(sbr_model* m, const sbr_hyper_values& hv, const uin
     return SBR_OK;
 }
 
-sbr_status sbr_model_restore(sbr_model* m, const char* path) {
+sbr_status sbr_model_restore(sbr_model* m, const char* path) try {
     if (!m || !path) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     sbr_status s = require_device();
     if (s) return s;
@@ -1263,9 +1263,9 @@ sbr_status sbr_model_restore(sbr_model* m, const char* path) {
     if ((s = ckpt_read(path, &hv, rs, &nu, &dir, &f))) return s;
     FileCloser fc{f};
     return ckpt_apply(m, hv, rs, nu, dir, f);
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_model_restore: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_model_restore: unknown C++ exception"); }
 
-sbr_status sbr_model_load(const char* path, sbr_model** out) {
+sbr_status sbr_model_load(const char* path, sbr_model** out) try {
     if (!path || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     sbr_status s = require_device();
     if (s) return s;
@@ -1284,7 +1284,7 @@ sbr_status sbr_model_load(const char* path, sbr_model** out) {
     if ((s = ckpt_apply(m, hv, rs, nu, dir, f))) { const std::string keep = g_err; sbr_model_free(m); g_err = keep; return s; }
     *out = m;
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_model_load: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_model_load: unknown C++ exception"); }
 
 // ---------------------------------------------------------------------------------- data.rs:54-88 splits ----
 // SipHash-2-4 (Aumasson & Bernstein) of one 8-byte little-endian word: what siphasher's `write_usize` + `finish` compute
@@ -1305,7 +1305,7 @@ static uint64_t siphash24_u64(uint64_t k0, uint64_t k1, uint64_t m) {
 }
 // data.rs:69-88 user_based_split: is_train(x) = siphash(key_0, key_1, user) % 100_000 > (test_fraction * 100_000) as u64,
 // the keys being two Uniform<u64>[0, MAX) draws from the caller's rng.  Host-only (data preparation of the tests / examples).
-sbr_status sbr_user_based_split(const uint64_t* user_ids, size_t nnz, uint32_t rng_state[4], float test_fraction, uint8_t* out_is_train) {
+sbr_status sbr_user_based_split(const uint64_t* user_ids, size_t nnz, uint32_t rng_state[4], float test_fraction, uint8_t* out_is_train) try {
     if ((nnz && (!user_ids || !out_is_train)) || !rng_state) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if ((rng_state[0] | rng_state[1] | rng_state[2] | rng_state[3]) == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "xorshift state must not be all zero");
     XorShift rng; rng.x = rng_state[0]; rng.y = rng_state[1]; rng.z = rng_state[2]; rng.w = rng_state[3];
@@ -1315,11 +1315,11 @@ sbr_status sbr_user_based_split(const uint64_t* user_ids, size_t nnz, uint32_t r
     for (size_t i = 0; i < nnz; ++i) out_is_train[i] = (siphash24_u64(k0, k1, user_ids[i]) % denominator) > cutoff;
     rng_state[0] = rng.x; rng_state[1] = rng.y; rng_state[2] = rng.z; rng_state[3] = rng.w;
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_user_based_split: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_user_based_split: unknown C++ exception"); }
 // data.rs:54-64 train_test_split: interactions.shuffle(rng) (Fisher-Yates from the top), then the FIRST
 // (test_fraction * len) as usize shuffled interactions are the test set.  perm[k] = original index of the k-th
 // shuffled interaction; perm[0 .. *num_test) is test, the rest is train.
-sbr_status sbr_train_test_split(size_t nnz, uint32_t rng_state[4], float test_fraction, uint64_t* perm, size_t* num_test) {
+sbr_status sbr_train_test_split(size_t nnz, uint32_t rng_state[4], float test_fraction, uint64_t* perm, size_t* num_test) try {
     if ((nnz && !perm) || !rng_state || !num_test) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if ((rng_state[0] | rng_state[1] | rng_state[2] | rng_state[3]) == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "xorshift state must not be all zero");
     XorShift rng; rng.x = rng_state[0]; rng.y = rng_state[1]; rng.z = rng_state[2]; rng.w = rng_state[3];
@@ -1328,12 +1328,12 @@ sbr_status sbr_train_test_split(size_t nnz, uint32_t rng_state[4], float test_fr
     *num_test = (size_t)(test_fraction * (float)nnz);
     rng_state[0] = rng.x; rng_state[1] = rng.y; rng_state[2] = rng.z; rng_state[3] = rng.w;
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_train_test_split: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_train_test_split: unknown C++ exception"); }
 
 // host-only view of the schedule that fit() builds (no device needed): lets CPU-only CI pin the chunker / filter /
 // master shuffle against the oracle
 sbr_status sbr_host_schedule(const sbr_compressed* c, size_t max_sequence_length, uint32_t rng_state[4], uint64_t* starts, uint32_t* lens,
-                             uint32_t* order, size_t cap, size_t* nsub) {
+                             uint32_t* order, size_t cap, size_t* nsub) try {
     if (!c || !rng_state || !nsub) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if ((rng_state[0] | rng_state[1] | rng_state[2] | rng_state[3]) == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "xorshift state must not be all zero");
     XorShift rng; rng.x = rng_state[0]; rng.y = rng_state[1]; rng.z = rng_state[2]; rng.w = rng_state[3];
@@ -1348,9 +1348,9 @@ sbr_status sbr_host_schedule(const sbr_compressed* c, size_t max_sequence_length
         rng_state[0] = rng.x; rng_state[1] = rng.y; rng_state[2] = rng.z; rng_state[3] = rng.w;
     }
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_host_schedule: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_host_schedule: unknown C++ exception"); }
 
-sbr_status sbr_host_master_schedule(uint32_t rng_state[4], size_t nsub, size_t partitions, size_t threads, uint32_t* order, uint64_t* keys) {
+sbr_status sbr_host_master_schedule(uint32_t rng_state[4], size_t nsub, size_t partitions, size_t threads, uint32_t* order, uint64_t* keys) try {
     if (!rng_state || !order || (partitions && !keys)) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if ((rng_state[0] | rng_state[1] | rng_state[2] | rng_state[3]) == 0) return fail(SBR_ERR_INVALID_ARGUMENT, "xorshift state must not be all zero");
     if (nsub > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "too many sub-sequences");
@@ -1359,14 +1359,14 @@ sbr_status sbr_host_master_schedule(uint32_t rng_state[4], size_t nsub, size_t p
     master_schedule(rng, order, nsub, partitions, rngs.data(), keys, threads);
     rng_state[0] = rng.x; rng_state[1] = rng.y; rng_state[2] = rng.z; rng_state[3] = rng.w;
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_host_master_schedule: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_host_master_schedule: unknown C++ exception"); }
 
 // --------------------------------------------------------------------------------------------------- fit ----
 // Order of business (everything the device can do is on the model's stream, the host never waits before the end):
 //   main thread : user_ptr -> HBM, device chunker (data_prep.cu) enqueued          | count sub-sequences (threads), master shuffle
 //   upload thread:                                  id stream -> HBM (narrowed)     |   of their indices into a pinned buffer,
 //   then: order / rngs / keys -> HBM from the pinned buffer; the plan is ready when the stream is.                partition rngs
-sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_plan** out) {
+sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_plan** out) try {
     if (!m || !c || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     sbr_status s = require_device();
     if (s) return s;
@@ -1491,9 +1491,9 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
 #undef CUP
     *out = pl;
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_fit_plan_create: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_fit_plan_create: unknown C++ exception"); }
 
-sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
+sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) try {
     if (!pl) return fail(SBR_ERR_INVALID_ARGUMENT, "null plan");
     sbr_status s = require_device();
     if (s) return s;
@@ -1563,7 +1563,7 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) {
     pl->stats.train_kernel_ms = kms; pl->stats.total_device_ms = tms;
     if (loss_out) *loss_out = total;
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_fit_plan_run: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_fit_plan_run: unknown C++ exception"); }
 
 sbr_status sbr_fit_plan_stats(const sbr_fit_plan* p, sbr_fit_stats* out) {
     if (!p || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
@@ -1571,7 +1571,7 @@ sbr_status sbr_fit_plan_stats(const sbr_fit_plan* p, sbr_fit_stats* out) {
     return SBR_OK;
 }
 sbr_status sbr_fit_plan_read_schedule(const sbr_fit_plan* p, uint64_t* starts, uint32_t* lens, uint32_t* order, size_t cap, size_t* nsub,
-                                      size_t* norder) {
+                                      size_t* norder) try {
     if (!p || !nsub || !norder) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     *nsub = p->nsub; *norder = p->P * p->n;
     if (!starts || !lens || !order || cap < p->nsub) return SBR_OK;
@@ -1584,7 +1584,7 @@ sbr_status sbr_fit_plan_read_schedule(const sbr_fit_plan* p, uint64_t* starts, u
     CU(cudaMemcpyAsync(order, p->dev.order, p->P * p->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_fit_plan_read_schedule: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_fit_plan_read_schedule: unknown C++ exception"); }
 void sbr_fit_plan_free(sbr_fit_plan* p) { if (p) { cudaSetDevice(g_device); delete p; } }
 
 sbr_status sbr_model_fit(sbr_model* m, const sbr_compressed* c, float* loss_out) {
@@ -1605,7 +1605,7 @@ sbr_status sbr_model_last_fit_stats(const sbr_model* m, sbr_fit_stats* out) {
 
 // --------------------------------------------------------------------------------------------- inference ----
 sbr_status sbr_model_user_representations(const sbr_model* m, const uint64_t* ptr, const uint64_t* item_ids, size_t num_users,
-                                          float* out) {
+                                          float* out) try {
     if (!m || !ptr || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before using it");
     sbr_status s = require_device();
@@ -1633,14 +1633,14 @@ sbr_status sbr_model_user_representations(const sbr_model* m, const uint64_t* pt
     if (s) return s;
     if (e != cudaSuccess) return cuda_fail(e, "user_representations");
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_model_user_representations: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_model_user_representations: unknown C++ exception"); }
 
 sbr_status sbr_model_user_representation(const sbr_model* m, const uint64_t* item_ids, size_t n, float* out) {
     const uint64_t ptr[2] = {0, (uint64_t)n};
     return sbr_model_user_representations(m, ptr, item_ids, 1, out);
 }
 
-sbr_status sbr_model_predict(const sbr_model* m, const float* user, const uint64_t* item_ids, size_t k, float* out) {
+sbr_status sbr_model_predict(const sbr_model* m, const float* user, const uint64_t* item_ids, size_t k, float* out) try {
     if (!m || !user || (k && (!item_ids || !out))) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before using it");
     sbr_status s = require_device();
@@ -1671,9 +1671,9 @@ sbr_status sbr_model_predict(const sbr_model* m, const float* user, const uint64
     if (e != cudaSuccess) return cuda_fail(e, "predict");
     if (flag) return fail(SBR_ERR_INVALID_PREDICTION, "Invalid prediction value: non-finite or not a number.");
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_model_predict: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_model_predict: unknown C++ exception"); }
 
-sbr_status sbr_model_mrr_score(const sbr_model* m, const sbr_compressed* test, float* out) {
+sbr_status sbr_model_mrr_score(const sbr_model* m, const sbr_compressed* test, float* out) try {
     if (!m || !test || !out) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
     if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before using it");
     sbr_status s = require_device();
@@ -1704,12 +1704,12 @@ sbr_status sbr_model_mrr_score(const sbr_model* m, const sbr_compressed* test, f
         if (test->up_[u + 1] - test->up_[u] >= 2) { sum += rr[u]; ++cnt; }
     *out = cnt ? sum / (float)cnt : NAN;
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_model_mrr_score: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_model_mrr_score: unknown C++ exception"); }
 
 // Stand-alone embedding gather timed on the device (BASELINE.json metric "embed-gather HBM GB/s"): the ids are uploaded
 // once, gather_rows_kernel runs 1 + iters times on the model's stream between CUDA events, *kernel_ms is the mean of the
 // timed launches.  Algorithmic bytes per row: 4 D read + 4 D written + 4 (u32 id).  `out` may be NULL (nothing copied back).
-sbr_status sbr_model_gather_rows_timed(const sbr_model* m, const uint64_t* item_ids, size_t n, float* out, int iters, double* kernel_ms) {
+sbr_status sbr_model_gather_rows_timed(const sbr_model* m, const uint64_t* item_ids, size_t n, float* out, int iters, double* kernel_ms) try {
     if (!m || !kernel_ms || iters < 1 || (n && !item_ids)) return fail(SBR_ERR_INVALID_ARGUMENT, "bad argument");
     if (!m->attached) return fail(SBR_ERR_INVALID_ARGUMENT, "sharded model: call sbr_model_ipc_attach before using it");
     sbr_status s = require_device();
@@ -1745,7 +1745,7 @@ sbr_status sbr_model_gather_rows_timed(const sbr_model* m, const uint64_t* item_
     if (s) return s;
     if (e != cudaSuccess) return cuda_fail(e, "gather_rows_timed");
     return SBR_OK;
-}
+} catch (const std::exception& e) { return fail(SBR_ERR_INVALID_ARGUMENT, std::string("sbr_model_gather_rows_timed: ") + e.what()); } catch (...) { return fail(SBR_ERR_INVALID_ARGUMENT, "sbr_model_gather_rows_timed: unknown C++ exception"); }
 
 sbr_status sbr_model_gather_rows(const sbr_model* m, const uint64_t* item_ids, size_t n, float* out) {
     if (!m || (n && (!item_ids || !out))) return fail(SBR_ERR_INVALID_ARGUMENT, "null argument");
