@@ -153,6 +153,47 @@ def wide_lstm_leg(pkg, name, rank, world, steps, barrier, max_over_ranks):
     return out
 
 
+def learnable_task_leg(pkg):
+    """Convergence evidence at the benchmarked concurrency (the uniform-random bench stream has nothing to learn): a catalogue of
+    the same shape whose sequences follow a noisy item -> item map (next = perm[cur] with p = 0.8, else uniform).  Test MRR of
+    the next item for 4,096 held-out users (mrr_score) after the automatic schedule's bounded first epoch and after two more
+    device-filling epochs, beside a model started cold at the device-filling partition count."""
+    N, L, S = NUM_ITEMS, SEQ_LEN, 1 << 20
+    rng = np.random.default_rng(77)
+    perm = rng.permutation(np.arange(1, N))
+
+    def chains(users, seed):
+        r = np.random.default_rng(seed)
+        out = np.empty((users, L), dtype=np.uint64)
+        cur = r.integers(1, N, size=users)
+        for t in range(L):
+            out[:, t] = cur
+            cur = np.where(r.random(users) >= 0.8, r.integers(1, N, size=users), perm[cur - 1])
+        return np.arange(users + 1, dtype=np.uint64) * np.uint64(L), out.reshape(-1)
+
+    ptr, ids = chains(S, 1)
+    tptr, tids = chains(4096, 2)
+    train = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N).upload()
+    test = pkg.CompressedInteractions.from_csr(tptr, tids, None, num_items=N).upload()
+
+    def build(threads):
+        return (pkg.lstm.Hyperparameters(N, L).embedding_dim(DIM).learning_rate(0.05).l2_penalty(0.0).loss(pkg.Loss.WARP)
+                .optimizer(pkg.Optimizer.Adagrad).lstm_variant(pkg.LSTMVariant.Normal).parallelism(pkg.Parallelism.Asynchronous)
+                .num_epochs(1).num_threads(threads).from_seed(bytes(range(16))).build())
+    m = build(0)
+    hist = []
+    for _ in range(3):
+        m.fit(train)
+        hist.append({"partitions": int(m.last_fit_stats()["partitions"]), "test_mrr": float(pkg.mrr_score(m, test))})
+    device_fill = hist[-1]["partitions"]
+    cold = build(device_fill)
+    for _ in range(3):
+        cold.fit(train)
+    return {"task": "noisy item->item chain, %d items, 2^20 x %d training users, 4096 test users; LSTM dim %d WARP Adagrad lr 0.05" % (N, L, DIM),
+            "automatic_num_threads_epochs": hist, "cold_start_at_%d_partitions_after_3_epochs_test_mrr" % device_fill: float(pkg.mrr_score(cold, test)),
+            "untrained_mrr": 0.005, "ceiling_mrr": 0.79}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -355,6 +396,11 @@ def main():
 
     # ---------------- device-resident arm: `value` ----------------
     data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=NUM_ITEMS).upload()
+    # Warm start (untimed): with num_threads = 0 a cold LSTM trains its first epoch at a bounded partition count
+    # (2.5 per item: 4,096 here) and fills the device afterwards -- from random parameters 37,888 concurrent sequences on
+    # 1,683 item rows do not learn.  The measured steps are device-filling epochs of a model that has had that first epoch.
+    model.fit(data)
+    warm_partitions = model.last_fit_stats()["partitions"]
     plan = model.fit_plan(data)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -389,6 +435,7 @@ def main():
         zptr, zids = make_stream(S, 2000 + rank, zipf=True)
         zdata = pkg.CompressedInteractions.from_csr(zptr, zids, None, num_items=NUM_ITEMS).upload()
         zmodel = hyper_factory().build()
+        zmodel.fit(zdata)
         zplan = zmodel.fit_plan(zdata)
         for _ in range(args.warmup):
             zplan.run()
@@ -438,6 +485,7 @@ def main():
     if os.environ.get("SBR_BENCH_C4", "1") != "0":
         c4 = sharded_c4_leg(pkg, torch, dist, rank, world, args.steps, args.warmup, barrier, max_over_ranks)
 
+    learn = learnable_task_leg(pkg) if (rank == 0 and os.environ.get("SBR_BENCH_LEARN", "1") != "0") else None
     wide = {}
     if os.environ.get("SBR_BENCH_WIDE", "1") != "0":
         for cname in ("c3", "c5"):
@@ -465,6 +513,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(config, seqs_per_gpu_per_step=S, partitions_per_gpu=int(partitions),
+                           warm_start="one untimed epoch at %d partitions (automatic num_threads on a cold LSTM, DESIGN 4.5), then device-filling" % warm_partitions,
                            parallelism=("hogwild partitions; one shared model, item table row-sharded over %d GPUs via NVLink peer access" % world)
                            if multi == "shared" else
                            ("hogwild partitions per GPU; full replica per GPU, deltas of parameters and Adagrad state summed over %d GPUs "
@@ -487,6 +536,8 @@ def main():
             out["sharded_c4"] = c4
         for cname, leg in wide.items():
             out[cname] = leg
+        if learn:
+            out["convergence"] = learn
         if zipf:
             out["zipf"] = zipf
         if world == 1:

@@ -256,6 +256,10 @@ sbr_status sbr_fit_plan_stats(const sbr_fit_plan* p, sbr_fit_stats* out);
 sbr_status sbr_fit_plan_read_schedule(const sbr_fit_plan* p, uint64_t* starts, uint32_t* lens, uint32_t* order, size_t cap, size_t* nsub,
                                       size_t* norder);
 void sbr_fit_plan_free(sbr_fit_plan* p);
+/* Changes Hyperparameters::num_threads of a built model for its following fits (0 = automatic).  Useful on small catalogues:
+ * an LSTM trains its first epoch at a bounded partition count and continues with a device-filling one (the
+ * automatic setting does exactly that). */
+sbr_status sbr_model_set_num_threads(sbr_model* m, size_t num_threads);
 /* stats of the most recent sbr_model_fit on this model */
 sbr_status sbr_model_last_fit_stats(const sbr_model* m, sbr_fit_stats* out);
 

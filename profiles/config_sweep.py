@@ -29,7 +29,10 @@ for name in (sys.argv[1:] or list(CONFIGS)):
     if kind == "lstm":
         h = h.lstm_variant(pkg.LSTMVariant.Normal)
     model = h.build()
-    plan = model.fit_plan(pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N).upload())
+    data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N).upload()
+    if kind == "lstm" and N < 10_000:
+        model.fit(data)    # automatic num_threads holds a cold LSTM on a small catalogue to 2.5 partitions per item for its first epoch
+    plan = model.fit_plan(data)
     plan.run()
     ms = []
     for _ in range(3):

@@ -39,7 +39,7 @@ EXPORTS = [
     "sbr_hyper_num_threads", "sbr_hyper_parallelism", "sbr_hyper_from_seed", "sbr_hyper_optimizer", "sbr_hyper_free",
     "sbr_hyper_build", "sbr_lstm_hyperparameters_random", "sbr_ewma_hyperparameters_random", "sbr_hyper_exact_arithmetic",
     "sbr_hyper_get_values", "sbr_model_get_hyper_values", "sbr_model_save", "sbr_model_load", "sbr_model_restore",
-    "sbr_model_fit", "sbr_model_user_representation", "sbr_model_user_representations", "sbr_model_predict",
+    "sbr_model_fit", "sbr_model_set_num_threads", "sbr_model_user_representation", "sbr_model_user_representations", "sbr_model_predict",
     "sbr_model_mrr_score", "sbr_model_gather_rows", "sbr_model_gather_rows_timed", "sbr_model_embedding_dim", "sbr_model_num_items",
     "sbr_model_parameter_len", "sbr_model_get_parameter", "sbr_model_set_parameter", "sbr_model_get_num_updates",
     "sbr_model_set_num_updates", "sbr_model_get_rng_state", "sbr_model_set_rng_state", "sbr_model_free",
@@ -183,6 +183,7 @@ def lib():
     L.sbr_model_ipc_export.argtypes = [vp, C.c_void_p]
     L.sbr_model_ipc_attach.argtypes = [vp, C.c_void_p]
     L.sbr_model_replica_sync.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.sbr_model_set_num_threads.argtypes = [vp, C.c_size_t]
     L.sbr_dist_unique_id.argtypes = [u8p]
     L.sbr_dist_init.argtypes = [C.c_int, C.c_int, u8p]
     L.sbr_dist_finalize.restype = None
@@ -641,6 +642,11 @@ class _Model:
     def restore(self, path):
         """overwrite parameters, optimizer state, rng and update counter from a checkpoint of the same shape"""
         _check(lib().sbr_model_restore(self._m, os.fsencode(path)))
+
+    def set_num_threads(self, n):
+        """sbr_model_set_num_threads: partition count of the following fits (0 = automatic)."""
+        _check(lib().sbr_model_set_num_threads(self._m, int(n)))
+        return self
 
     def replica_sync(self):
         """sbr_model_replica_sync: sum of all ranks' parameter / optimizer-state deltas applied to every replica; returns the bytes all-reduced."""

@@ -323,6 +323,8 @@ struct sbr_fit_plan {
     SyncBuffers* sync = nullptr;
     BatchBuffers* batch = nullptr;
     bool use_batch = false;   // LSTM on the round-synchronous batched tensor-core engine (lstm_batch.cuh)
+    bool cold_bounded = false;   // automatic partition count was held down because the model is still cold
+    int epochs_override = -1;    // >= 0: run this many epochs instead of hyper.num_epochs
     ~sbr_fit_plan() {
         if (sync) sync_buffers_free(sync);
         if (batch) batch_buffers_free(batch);
@@ -1382,6 +1384,7 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
     if (nsub > 0xffffffffull) return fail(SBR_ERR_INVALID_ARGUMENT, "too many sub-sequences");
     // :90-98 partitions
     size_t P = m->h.num_threads;
+    bool cold_bounded = false;
     if (P == 0) {
         const size_t autoP = (size_t)train_auto_partitions(m->dev, device_info().sms);
         P = std::min(autoP, std::max<size_t>(1, nsub / 16));
@@ -1389,13 +1392,21 @@ sbr_status sbr_fit_plan_create(sbr_model* m, const sbr_compressed* c, sbr_fit_pl
         // (nsub / 16 is almost never a multiple of 128) still runs on them
         if (m->dev.D == 32 && !m->dev.exact) { if (P >= 256) P -= P % 256; else if (P >= 128) P = 128; }
         if (m->dev.model == MODEL_LSTM && m->dev.D > 32 && !m->dev.exact && P >= 128) P -= P % 128;
+        // Cold-start bound.  An LSTM that starts from random parameters cannot absorb thousands of concurrent
+        // sequences per item row: before the first feedback every row takes hundreds of coherent Adagrad steps (scale-invariant:
+        // lr-sized whatever the gradient's size), embeddings and gate weights blow up together and the cell saturates for
+        // good (measured: 1,683 items, 37,888 partitions: MRR stays at the untrained level for 64 epochs; <= 4,096 partitions
+        // learn in one epoch; a warm model trains fine at 37,888).  Until the model has seen ~100 steps per item the automatic
+        // choice therefore stays below 2.5 partitions per item; afterwards it fills the device.
+        const size_t bound = std::max<size_t>(256, (size_t)(2.5 * (double)m->dev.N) / 256 * 256);
+        if (m->dev.model == MODEL_LSTM && m->num_updates < 100ull * m->dev.N && P > bound) { P = bound; cold_bounded = true; }
     }
     if (P > nsub) return fail(SBR_ERR_INVALID_ARGUMENT, "num_threads exceeds the number of sub-sequences (the reference panics in chunks_mut(0))");
     const size_t n = nsub / P;  // :91, remainder dropped by the zip at :94-96
 
     sbr_fit_plan* pl = new (std::nothrow) sbr_fit_plan();
     if (!pl) return fail(SBR_ERR_INVALID_ARGUMENT, "out of memory");
-    pl->model = m; pl->nsub = nsub; pl->P = P; pl->n = n;
+    pl->model = m; pl->nsub = nsub; pl->P = P; pl->n = n; pl->cold_bounded = cold_bounded;
     {   // which engine: LSTM under Parallelism::Synchronous (any width), and the wide LSTMs with many partitions, run in rounds
         const char* why = nullptr;
         const bool can = m->dev.model == MODEL_LSTM && m->h.shard_world <= 1 && batch_lstm_supported(m->dev, (uint32_t)P, &why);
@@ -1501,7 +1512,7 @@ sbr_status sbr_fit_plan_run(sbr_fit_plan* pl, float* loss_out) try {
     std::lock_guard<std::mutex> lk(m->mu);
     cudaStream_t st = m->stream;
     const size_t P = pl->P;
-    pl->dev.epochs = (int)m->h.num_epochs;
+    pl->dev.epochs = pl->epochs_override >= 0 ? pl->epochs_override : (int)m->h.num_epochs;
     pl->dev.adam_t0 = m->num_updates;
     CU(cudaMemsetAsync(pl->dev.loss_acc, 0, P * sizeof(float), st));
     CU(cudaMemsetAsync(pl->dev.examples, 0, P * sizeof(unsigned long long), st));
@@ -1591,10 +1602,30 @@ sbr_status sbr_model_fit(sbr_model* m, const sbr_compressed* c, float* loss_out)
     sbr_fit_plan* pl = nullptr;
     sbr_status s = sbr_fit_plan_create(m, c, &pl);
     if (s) return s;
+    // automatic partitions on a cold model: the first epoch runs at the bounded count, the remaining epochs
+    // on a second schedule at whatever the (now warmer) model allows; the returned loss is the second schedule's
+    const bool split = pl->cold_bounded && m->h.num_epochs > 1;
+    if (split) pl->epochs_override = 1;
     s = sbr_fit_plan_run(pl, loss_out);
     if (s == SBR_OK) m->last = pl->stats;
     sbr_fit_plan_free(pl);
+    if (s == SBR_OK && split) {
+        pl = nullptr;
+        s = sbr_fit_plan_create(m, c, &pl);
+        if (s) return s;
+        pl->epochs_override = (int)m->h.num_epochs - 1;
+        s = sbr_fit_plan_run(pl, loss_out);
+        if (s == SBR_OK) m->last = pl->stats;
+        sbr_fit_plan_free(pl);
+    }
     return s;
+}
+
+sbr_status sbr_model_set_num_threads(sbr_model* m, size_t num_threads) {
+    if (!m) return fail(SBR_ERR_INVALID_ARGUMENT, "null model");
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->h.num_threads = num_threads;
+    return SBR_OK;
 }
 
 sbr_status sbr_model_last_fit_stats(const sbr_model* m, sbr_fit_stats* out) {

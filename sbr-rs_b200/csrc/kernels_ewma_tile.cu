@@ -82,20 +82,22 @@ __device__ __forceinline__ void red_add4(float* p, const float4& v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-struct OptC { float lr, l2, c1, c2; };
+struct OptC { float lr, l2, c1, c2; float chat; };
 // Adagrad on a pair of elements, as deltas: g' = g + l2 w ; dG = g'^2 ; dw = -lr g' / sqrt(G + dG)   (w, G are updated too)
 __device__ __forceinline__ void adagrad2(float2& w, float2& G, const float2& g, const OptC& o, float2& dw, float2& dG) {
     const float2 gg = fma2(w, splat2(o.l2), g);
     dG = mul2(gg, gg);
     G = add2(G, dG);
-    const float2 rs = make_float2(rsqrt_approx(fmaxf(G.x, 1e-20f)), rsqrt_approx(fmaxf(G.y, 1e-20f)));
+    // cold start under massive concurrency (o.chat = expected concurrent visitors of a row, 0 when <= 1): a visitor that finds
+    // the accumulator (nearly) empty is one of ~chat visitors that all see it empty; each steps as if its peers' g^2 were in
+    const float2 rs = make_float2(rsqrt_approx(fmaxf(G.x, fmaxf(o.chat * dG.x, 1e-20f))), rsqrt_approx(fmaxf(G.y, fmaxf(o.chat * dG.y, 1e-20f))));
     dw = mul2(mul2(gg, splat2(-o.lr)), rs);
     w = add2(w, dw);
 }
 __device__ __forceinline__ void adagrad1(float& w, float& G, float g, const OptC& o) {
     g = fmaf(w, o.l2, g);
     G = fmaf(g, g, G);
-    w = fmaf(-o.lr * g, rsqrt_approx(fmaxf(G, 1e-20f)), w);
+    w = fmaf(-o.lr * g, rsqrt_approx(fmaxf(G, fmaxf(o.chat * g * g, 1e-20f))), w);
 }
 __device__ __forceinline__ void adam1(float& w, float& m, float& v, float g, const OptC& o) {
     g = fmaf(w, o.l2, g);
@@ -196,6 +198,10 @@ __global__ void __launch_bounds__(256 * NT, 1) ewma_tile_train_kernel(ModelDev m
     uint64_t step = pl.step_ctr[live ? p : 0];
     if (live) { key = pl.keys[p]; ord = pl.order + (size_t)p * pl.n; }
     OptC o; o.lr = m.lr; o.l2 = m.l2; o.c1 = 1.0f; o.c2 = 1.0f;
+    {   // expected concurrent visitors of an item row (see kernels_lstm_tile.cu)
+        const float c = 3.0f * (float)pl.P / (float)m.N;
+        o.chat = c > 1.0f ? c : 0.0f;
+    }
     const int tries = m.loss == 2 ? 5 : 1;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float* alpha = m.dense + part * DPT;

@@ -123,11 +123,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar_smem, uint32_
 
 // one element of a sparse Adagrad / Adam visit on register copies; returns the step in w (the additive deltas of the
 // state are what the caller accumulates: G' - G resp. m' - m, v' - v)
-struct OptC { float lr, l2, c1, c2; int adam; };
+struct OptC { float lr, l2, c1, c2; int adam; float chat; };
 __device__ __forceinline__ void adagrad1(float& w, float& G, float g, const OptC& o) {
     g = fmaf(w, o.l2, g);
     G = fmaf(g, g, G);
-    w = fmaf(-o.lr * g, rsqrt_approx(fmaxf(G, 1e-20f)), w);   // lr / (1e-10 + sqrt(G)) * g
+    w = fmaf(-o.lr * g, rsqrt_approx(fmaxf(G, fmaxf(o.chat * g * g, 1e-20f))), w);   // lr / (1e-10 + sqrt(G)) * g
 }
 __device__ __forceinline__ void adam1(float& w, float& m, float& v, float g, const OptC& o) {
     g = fmaf(w, o.l2, g);
@@ -148,7 +148,9 @@ __device__ __forceinline__ void adagrad2(float2& w, float2& G, const float2& g, 
     const float2 gg = fma2(w, splat2(o.l2), g);
     dG = mul2(gg, gg);
     G = add2(G, dG);
-    const float2 rs = make_float2(rsqrt_approx(fmaxf(G.x, 1e-20f)), rsqrt_approx(fmaxf(G.y, 1e-20f)));
+    // cold start under massive concurrency (o.chat = expected concurrent visitors of a row, 0 when <= 1): a visitor that finds
+    // the accumulator (nearly) empty is one of ~chat visitors that all see it empty; each steps as if its peers' g^2 were in
+    const float2 rs = make_float2(rsqrt_approx(fmaxf(G.x, fmaxf(o.chat * dG.x, 1e-20f))), rsqrt_approx(fmaxf(G.y, fmaxf(o.chat * dG.y, 1e-20f))));
     dw = mul2(mul2(gg, splat2(-o.lr)), rs);
     w = add2(w, dw);
 }
@@ -306,6 +308,10 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
     if (live) { key = pl.keys[p]; ord = pl.order + (size_t)p * pl.n; }
     constexpr bool ADAM = S == 3;   // 400-byte records <=> Adam
     OptC o; o.lr = m.lr; o.l2 = m.l2; o.adam = ADAM ? 1 : 0; o.c1 = 1.0f; o.c2 = 1.0f;
+    {   // expected concurrent visitors of an item row: 3 visits per partition-timestep over m.N rows (DESIGN 3.4 "cold start")
+        const float c = 3.0f * (float)pl.P / (float)m.N;
+        o.chat = c > 1.0f ? c : 0.0f;
+    }
     const int tries = m.loss == 2 ? 5 : 1;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -751,6 +757,7 @@ __global__ void __launch_bounds__(256 * NT, 1) lstm_tile_train_kernel(ModelDev m
             }
             if (tile == 0) {
                 OptC od = o;
+                od.chat = 0.0f;   // dense weights: one read-modify-write per CTA round, last writer wins
                 if (od.adam) {
                     const float tt_ = (float)(pl.adam_t0 + step * pl.P + (uint64_t)blockIdx.x * NT * 128 + 1);
                     od.c1 = 1.0f - powf(0.9f, tt_); od.c2 = 1.0f - powf(0.999f, tt_);

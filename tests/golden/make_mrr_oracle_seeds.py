@@ -47,10 +47,10 @@ def split(O):
 
 def one(job):
     import oracle_lib as O
-    kind, s, threads = job
+    kind, s, threads, par = job
     tr, te = split(O)
     m = O.OracleModel(kind, N, T, embedding_dim=D, learning_rate=LR, l2_penalty=L2, lstm_variant="normal", loss="warp",
-                      optimizer="adagrad", parallelism="asynchronous", num_threads=threads, num_epochs=EPOCHS,
+                      optimizer="adagrad", parallelism=par, num_threads=threads, num_epochs=EPOCHS,
                       seed=bytes([s + 1] * 16))
     for k, v in initial_parameters(kind, s).items():
         m.param(k)[:] = v
@@ -66,15 +66,18 @@ if __name__ == "__main__":
     ap.add_argument("--procs", type=int, default=os.cpu_count())
     ap.add_argument("--threads", type=int, default=1, help="> 1: the oracle's Hogwild mode (lock-free pthreads; NOT deterministic); "
                     "results are added to the JSON under <kind>_hogwild<threads>")
+    ap.add_argument("--synchronous", action="store_true", help="with --threads > 1: Parallelism::Synchronous (the oracle's barrier mode, "
+                    "deterministic; the reference default, lstm.rs:66); results under <kind>_sync<threads>")
     a = ap.parse_args()
     import oracle_lib as O
     O.lib()
+    par = "synchronous" if a.synchronous else "asynchronous"
     with mp.Pool(a.procs) as pool:
-        res = pool.map(one, [(k, s, a.threads) for k in ("lstm", "ewma") for s in range(a.seeds)], chunksize=1)
+        res = pool.map(one, [(k, s, a.threads, par) for k in ("lstm", "ewma") for s in range(a.seeds)], chunksize=1)
     path = os.path.join(HERE, "mrr_oracle_seeds.json")
     out = json.load(open(path)) if (a.threads > 1 and os.path.exists(path)) else {}
     out["recipe"] = "ML-100K split [42;16] 0.2, seq %d dim %d WARP Adagrad lr %g l2 %g Normal, %d epochs, 1 thread" % (T, D, LR, L2, EPOCHS)
-    sfx = "" if a.threads == 1 else "_hogwild%d" % a.threads
+    sfx = "" if a.threads == 1 else ("_sync%d" if a.synchronous else "_hogwild%d") % a.threads
     for k in ("lstm", "ewma"):
         out[k + sfx] = [m for kk, s, m in sorted(res, key=lambda r: (r[0], r[1])) if kk == k]
         print(k + sfx, "mean %.4f sd %.4f n %d" % (np.mean(out[k + sfx]), np.std(out[k + sfx], ddof=1), len(out[k + sfx])))

@@ -193,3 +193,65 @@ def test_tile_kernel_learns_like_the_exact_path(pkg, oracle, loss, optimizer, lr
     assert b[-1] < b[0]
     # Adam's normalised steps amplify the bf16 / tf32 rounding of the first gradients: wider band for that case
     assert np.max(np.abs(a - b)) < (0.02 if optimizer == "adagrad" else 0.08), (a, b)
+
+
+def test_device_filling_hogwild_needs_a_warm_model_and_the_automatic_setting_provides_it(pkg):
+    """bench.py runs the tile kernel with 37,888 concurrent Hogwild partitions; real ML-100K has ~2.8 K sub-sequences, so the
+    MRR-parity tests stop at 128.  Convergence at the benchmarked concurrency, on a synthetic catalogue of the same shape (1,683
+    items, 2^20 users x 32 items) whose sequences follow a noisy item -> item map (next = perm[cur] with p = 0.8, else uniform),
+    which a sequence model can learn (MRR ~0.79; untrained ~0.005):
+      * from RANDOM parameters 37,888 partitions do not learn (measured, DESIGN 4.5: before the first feedback every item row
+        takes hundreds of coherent lr-sized Adagrad steps, embeddings and gate weights blow up together, the cell saturates);
+      * num_threads = 0 (automatic) therefore holds a cold LSTM below 2.5 partitions per item (4,096 here) for its first epoch
+        and fills the device afterwards: the first epoch learns the task, the following device-filling epochs keep it."""
+    N, L, S = 1683, 32, 1 << 20
+    rng = np.random.default_rng(77)
+    perm = rng.permutation(np.arange(1, N))                       # perm[i - 1] = successor of item i
+
+    def chains(users, seed):
+        r = np.random.default_rng(seed)
+        out = np.empty((users, L), dtype=np.uint64)
+        cur = r.integers(1, N, size=users)
+        for t in range(L):
+            out[:, t] = cur
+            nxt = perm[cur - 1]
+            noise = r.random(users) >= 0.8
+            cur = np.where(noise, r.integers(1, N, size=users), nxt)
+        return (np.arange(users + 1, dtype=np.uint64) * np.uint64(L)), out.reshape(-1)
+
+    ptr, ids = chains(S, 1)
+    tptr, tids = chains(4096, 2)
+    train = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N).upload()
+    test = pkg.CompressedInteractions.from_csr(tptr, tids, None, num_items=N).upload()
+
+    def build(threads):
+        return (pkg.lstm.Hyperparameters(N, L).embedding_dim(32).learning_rate(0.05).l2_penalty(0.0).loss(pkg.Loss.WARP)
+                .optimizer(pkg.Optimizer.Adagrad).lstm_variant(pkg.LSTMVariant.Normal).parallelism(pkg.Parallelism.Asynchronous)
+                .num_epochs(1).num_threads(threads).from_seed(bytes(range(16))).build())
+
+    auto = build(0)
+    hist = []
+    for _ in range(3):
+        auto.fit(train)
+        st = auto.last_fit_stats()
+        assert st["kernel"].startswith("lstm_tile_train_kernel"), st
+        hist.append((st["partitions"], pkg.mrr_score(auto, test)))
+    assert hist[0][0] == 4096 and hist[1][0] == 37888 and hist[2][0] == 37888, hist
+    assert hist[0][1] > 0.6 and min(hist[1][1], hist[2][1]) > hist[0][1] - 0.03, hist
+    for n in ("item_embeddings", "lstm_weights"):
+        assert np.all(np.isfinite(auto.get_parameter(n))), n
+    # the same through one fit() of three epochs: first epoch bounded, the other two on a second, device-filling schedule
+    three = (pkg.lstm.Hyperparameters(N, L).embedding_dim(32).learning_rate(0.05).l2_penalty(0.0).loss(pkg.Loss.WARP)
+             .optimizer(pkg.Optimizer.Adagrad).lstm_variant(pkg.LSTMVariant.Normal).parallelism(pkg.Parallelism.Asynchronous)
+             .num_epochs(3).num_threads(0).from_seed(bytes(range(16))).build())
+    three.fit(train)
+    assert three.last_fit_stats()["partitions"] == 37888 and three.num_updates > 2 * (1 << 20)
+    assert pkg.mrr_score(three, test) > 0.6
+    # and the measured fact behind the policy: a cold model at the device-filling count stays untrained
+    cold = build(37888)
+    for _ in range(3):
+        cold.fit(train)
+    assert cold.last_fit_stats()["partitions"] == 37888
+    cold_mrr = pkg.mrr_score(cold, test)
+    print("cold start at 37,888 partitions: MRR %.4f; automatic (4,096 then 37,888): %s" % (cold_mrr, hist))
+    assert cold_mrr < 0.5 * hist[2][1], (cold_mrr, hist)

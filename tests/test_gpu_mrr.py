@@ -10,6 +10,9 @@ initial parameters and the same model rng (tests/golden/make_mrr_oracle_seeds.py
   gpu exact       libsbr_b200, num_threads 1: the oracle's update order, exact fp32 kernels
   gpu hogwild-32  32 Hogwild partitions (reference: num_threads > 1)
   gpu tile-128    LSTM only: the tcgen05 tile kernel, 128 partitions -- the kernel bench.py measures
+  gpu sync-16     Parallelism::Synchronous with 16 threads -- the reference's DEFAULT mode (lstm.rs:66-68 on a 16-core host):
+                  the round engines (sync_engine.cu for EWMA, the batched tcgen05 engine of lstm_batch.cuh for LSTM), compared
+                  with the oracle's own barrier mode at 16 threads (golden key <kind>_sync16; deterministic on both sides)
 
 One run's MRR has a spread of ~0.01 over seeds, so the standard error of a difference of two SEEDS-seed means is
 ~0.002: the assertion is |mean(arm) - mean(oracle)| <= 2 s.e. of the paired difference (+ a 0.001 floor for the exact
@@ -50,7 +53,7 @@ def test_mrr_matches_oracle_over_seeds(pkg, oracle, ml100k, kind):
     tr, te = _split(oracle, ml100k)
     train = pkg.CompressedInteractions.from_csr(tr[0], tr[1], None, num_items=G.N).upload()
     test = pkg.CompressedInteractions.from_csr(te[0], te[1], None, num_items=G.N).upload()
-    arms = {"gpu_exact_1thread": 1, "gpu_hogwild_32": 32}
+    arms = {"gpu_exact_1thread": 1, "gpu_hogwild_32": 32, "gpu_sync_16": 16}
     if kind == "lstm":
         arms["gpu_tile_kernel_128"] = 128
 
@@ -58,7 +61,8 @@ def test_mrr_matches_oracle_over_seeds(pkg, oracle, ml100k, kind):
         H = pkg.lstm.Hyperparameters if kind == "lstm" else pkg.ewma.Hyperparameters
         h = (H(G.N, G.T).embedding_dim(G.D).learning_rate(G.LR).l2_penalty(G.L2).loss(pkg.Loss.WARP)
              .optimizer(pkg.Optimizer.Adagrad).num_epochs(G.EPOCHS).num_threads(threads)
-             .parallelism(pkg.Parallelism.Asynchronous).from_seed(bytes([s + 1] * 16)))
+             .parallelism(pkg.Parallelism.Synchronous if arm == "gpu_sync_16" else pkg.Parallelism.Asynchronous)
+             .from_seed(bytes([s + 1] * 16)))
         if kind == "lstm":
             h = h.lstm_variant(pkg.LSTMVariant.Normal)
         if arm == "gpu_hogwild_32":
@@ -69,6 +73,8 @@ def test_mrr_matches_oracle_over_seeds(pkg, oracle, ml100k, kind):
         m.fit(train)
         st = m.last_fit_stats()
         assert st["partitions"] == threads
+        if arm == "gpu_sync_16":
+            assert ("batched" if kind == "lstm" else "round-synchronous") in st["kernel"], st["kernel"]
         return arm, s, pkg.mrr_score(m, test)
 
     # the single-warp fits of the exact arm overlap: every model has its own stream and ctypes releases the GIL
@@ -84,6 +90,11 @@ def test_mrr_matches_oracle_over_seeds(pkg, oracle, ml100k, kind):
         hog = np.array(gj[kind + "_hogwild32"][:SEEDS])
         out["oracle_hogwild_32"] = {"mean": float(hog.mean()), "sd": float(hog.std(ddof=1)), "se": float(hog.std(ddof=1) / np.sqrt(len(hog))),
                                     "values": hog.tolist()}
+    syn = None
+    if kind + "_sync16" in gj:
+        syn = np.array(gj[kind + "_sync16"][:SEEDS])
+        out["oracle_sync_16"] = {"mean": float(syn.mean()), "sd": float(syn.std(ddof=1)), "se": float(syn.std(ddof=1) / np.sqrt(len(syn))),
+                                 "values": syn.tolist()}
     ok = True
     for arm in arms:
         v = np.array([m for a, s, m in sorted(res, key=lambda r: r[1]) if a == arm])
@@ -97,7 +108,16 @@ def test_mrr_matches_oracle_over_seeds(pkg, oracle, ml100k, kind):
         print("%s %-22s mean %.4f  oracle %.4f  delta %+.4f +- %.4f (1 s.e.)  +-0.002 met: %s" % (
             kind, arm, v.mean(), gold.mean(), d.mean(), se_d, out[arm]["north_star_band_0.002_met"]))
         ok = ok and out[arm]["within_2se"]
-        if hog is not None and arm != "gpu_exact_1thread":
+        if arm == "gpu_sync_16" and syn is not None and len(syn) == SEEDS:
+            ds_ = v - syn                      # same seeds, same schedule, deterministic on both sides: a paired difference
+            se_s = float(ds_.std(ddof=1) / np.sqrt(SEEDS))
+            out[arm]["delta_vs_oracle_sync_16"] = float(ds_.mean())
+            out[arm]["se_of_delta_vs_oracle_sync_16"] = se_s
+            out[arm]["north_star_band_0.002_met_vs_oracle_sync_16"] = bool(abs(ds_.mean()) <= 0.002)
+            out[arm]["max_abs_seed_delta_vs_oracle_sync_16"] = float(np.abs(ds_).max())
+            print("%s %-22s vs the oracle's own 16-thread barrier mode %.4f: delta %+.4f +- %.4f, largest per-seed |delta| %.4f" % (
+                kind, arm, syn.mean(), ds_.mean(), se_s, np.abs(ds_).max()))
+        elif hog is not None and arm != "gpu_exact_1thread":
             dh = float(v.mean() - hog.mean())
             se_h = float(np.sqrt(v.var(ddof=1) / len(v) + hog.var(ddof=1) / len(hog)))
             out[arm]["delta_vs_oracle_hogwild_32"] = dh
@@ -117,3 +137,7 @@ def test_mrr_matches_oracle_over_seeds(pkg, oracle, ml100k, kind):
     for arm in arms:
         if arm != "gpu_exact_1thread":
             assert abs(out[arm]["delta_vs_oracle"]) <= 0.01, (arm, out[arm]["delta_vs_oracle"])
+    # the Synchronous engines against the oracle's own barrier mode, seed by seed: the means agree statistically
+    if "delta_vs_oracle_sync_16" in out["gpu_sync_16"]:
+        a16 = out["gpu_sync_16"]
+        assert abs(a16["delta_vs_oracle_sync_16"]) <= 2 * a16["se_of_delta_vs_oracle_sync_16"] + 0.001, a16
