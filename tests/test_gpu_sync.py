@@ -97,3 +97,28 @@ def test_synchronous_never_falls_back_to_hogwild_silently(pkg):
          .from_seed(bytes(range(16))).virtual_shards(2).build())
     with pytest.raises(pkg.SbrError):
         m.fit(pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=100))
+
+
+@pytest.mark.parametrize("loss,P", [("bpr", 8), ("warp", 16)])
+def test_synchronous_rounds_with_colliding_rows_match_oracle(pkg, oracle, loss, P):
+    """A catalogue so small that several partitions of a round name the same rows (as on ML-100K): the entries of a row are
+    applied un-merged in the reference order -- thread-major, then t descending, E[neg], E[out], E[in] -- so the result is still
+    the oracle's barrier mode element for element (optimizer state started at 1: see tests/test_gpu_lstm_batch.py)."""
+    rng = np.random.default_rng(17)
+    N, T, D, U = 120, 10, 32, 64
+    lens = rng.integers(3, 25, size=U)
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    ids = rng.integers(1, N, size=int(ptr[-1])).astype(np.uint64)
+    gm, om = make_pair(pkg, oracle, "ewma", N, T, D, loss=loss, optimizer="adagrad", lr=0.05, l2=1e-3, epochs=2, threads=P,
+                       parallelism="synchronous", scale=0.3)
+    for n in om.param_names():
+        gm.set_parameter(n + ".s1", np.ones(len(gm.get_parameter(n)), dtype=np.float32))
+    for n in state_names(om, "adagrad"):
+        om.param(n)[:] = gm.get_parameter(n)
+    data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=N)
+    gl = gm.fit(data)
+    rc, ol = om.fit(ptr, ids)
+    assert rc == 0
+    diffs = max_abs_diff(gm, om, state_names(om, "adagrad"))
+    assert max(diffs.values()) <= 3e-4, diffs
+    assert abs(gl - ol) <= 1e-4 * max(1.0, abs(ol))
