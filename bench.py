@@ -242,6 +242,10 @@ class ClockSampler:
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         inside = [r for ts, r in self.rows if self.t0 is not None and self.t0 <= ts <= (self.t1 or ts) + 0.03]
+        in_region = len(inside)
+        if not inside and self.rows and self.t0 is not None:   # a region shorter than the sampling period: the rows closest to it
+            mid = 0.5 * (self.t0 + (self.t1 or self.t0))
+            inside = [r for _, r in sorted(self.rows, key=lambda tr: abs(tr[0] - mid))[:2]]
         for r in inside:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
@@ -251,7 +255,7 @@ class ClockSampler:
                 if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": in_region}
 
 
 def cpu_reference_run(num_seqs, steps, warmup, threads, seed=1234):
@@ -347,6 +351,8 @@ def main():
         raise SystemExit("bench.py needs a B200: libsbr_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     pkg.set_device(local_rank)
+    sampler = ClockSampler(local_rank)   # (nvidia-smi takes a few hundred ms to deliver its first row: started long before the timed region)
+    sampler.start()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -402,8 +408,6 @@ def main():
     model.fit(data)
     warm_partitions = model.last_fit_stats()["partitions"]
     plan = model.fit_plan(data)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     for _ in range(args.warmup):
         plan.run()
         if sync:
