@@ -577,6 +577,8 @@ int run_batch_lstm(const ModelDev& m, PlanDev& pl, BatchBuffers& B, uint64_t num
     uint32_t* v_in = static_cast<uint32_t*>(B.vals_in.p); uint32_t* v_out = static_cast<uint32_t*>(B.vals_out.p);
     uint64_t rounds_done = 0;
     *rounds_out = (uint64_t)pl.n * (uint64_t)pl.epochs;
+    int key_bits = 33;   // radix passes only over the bits in use: 32 order bits + the row id (unused slots are all ones: still last)
+    while (key_bits < 64 && (m.N >> (key_bits - 32)) != 0) ++key_bits;
     for (int ep = 0; ep < pl.epochs; ++ep) {
         sync_shuffle_kernel<<<(pl.P + 127) / 128, 128, 0, st>>>(pl);
         ++*launches;
@@ -597,7 +599,7 @@ int run_batch_lstm(const ModelDev& m, PlanDev& pl, BatchBuffers& B, uint64_t num
             bl_dw_kernel<<<g_dw, kGemmThreads, smem_dw, st>>>(bd, bp, nsplit);
             bl_keys_kernel<<<148 * 4, 256, 0, st>>>(pl, bd, bp, k_in, v_in);
             size_t tmp = B.cub_tmp.cap;
-            SCU(cub::DeviceRadixSort::SortPairs(B.cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (int)nslots, 0, 64, st));
+            SCU(cub::DeviceRadixSort::SortPairs(B.cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (int)nslots, 0, key_bits, st));
             const uint64_t t_adam = num_updates + (rounds_done + 1) * (uint64_t)pl.P;
             if (o.adam) { o.c1 = 1.0f - powf(0.9f, (float)t_adam); o.c2 = 1.0f - powf(0.999f, (float)t_adam); }
             SYNC_DISPATCH_D(D, sync_apply_kernel<kD><<<148 * 8, 256, 0, st>>>(m, 0, k_out, v_out, bp.grads, bp.bgrads, nslots, o));
