@@ -103,10 +103,16 @@ sbr_status sbr_hyper_embedding_dim(sbr_hyperparameters* h, size_t v);     /* lst
 sbr_status sbr_hyper_num_epochs(sbr_hyperparameters* h, size_t v);        /* lstm.rs:92-95 */
 sbr_status sbr_hyper_loss(sbr_hyperparameters* h, sbr_loss v);            /* lstm.rs:98-101 */
 sbr_status sbr_hyper_lstm_variant(sbr_hyperparameters* h, sbr_lstm_variant v); /* lstm.rs:104-107 (LSTM only) */
-/* lstm.rs:110-113.  On the GPU `num_threads` is the number of Hogwild partitions (one warp each) that train
- * concurrently; 0 = auto (fill the device).  1 reproduces the reference's single-thread update order exactly. */
+/* lstm.rs:110-113.  On the GPU `num_threads` is the number of partitions ("threads" of sequence_model.rs:90-98) that train
+ * concurrently.  1 reproduces the reference's single-thread update order exactly.  0 = automatic: fill the device, but never
+ * more than the data allows (sub-sequences / 16) and -- for an LSTM that has seen fewer than ~100 steps per item -- never more
+ * than 2.5 partitions per item: a cold LSTM does not learn with thousands of concurrent sequences per item row;
+ * a multi-epoch fit of a cold model runs its first epoch at the bounded count and the rest device-filling. */
 sbr_status sbr_hyper_num_threads(sbr_hyperparameters* h, size_t v);
-sbr_status sbr_hyper_parallelism(sbr_hyperparameters* h, sbr_parallelism v); /* lstm.rs:116-119 */
+/* lstm.rs:116-119.  Asynchronous = Hogwild.  Synchronous (the reference default) with num_threads > 1 runs in rounds: gradients
+ * from the round-start parameters, entries applied un-merged in thread order, one dense step per round (EWMA: 1..8 GPUs, WARP on
+ * one GPU; LSTM: one GPU, every loss).  Configurations the round engines cannot run return SBR_ERR_INVALID_ARGUMENT. */
+sbr_status sbr_hyper_parallelism(sbr_hyperparameters* h, sbr_parallelism v);
 sbr_status sbr_hyper_from_seed(sbr_hyperparameters* h, const uint8_t seed[16]); /* lstm.rs:129-132 */
 sbr_status sbr_hyper_optimizer(sbr_hyperparameters* h, sbr_optimizer v);  /* lstm.rs:135-138 */
 /* Hyperparameters::random(num_items, rng) (lstm.rs:141-172 / ewma.rs:139-170), "useful for hyperparameter search":
