@@ -1342,6 +1342,9 @@ sbr_status sbr_host_schedule(const sbr_compressed* c, size_t max_sequence_length
     std::vector<uint64_t> st; std::vector<uint32_t> ln, od;
     sbr_status s = host_schedule(c, max_sequence_length, rng, st, ln, od);
     if (s) return s;
+    // fit() itself only counts the sub-sequences on the host (the chunks are built on the device): the count it would use
+    // must be the number of chunks this one-thread reference pass produced
+    if (host_count_subsequences(c, max_sequence_length) != st.size()) return fail(SBR_ERR_INVALID_ARGUMENT, "internal: threaded sub-sequence count disagrees with the chunker");
     *nsub = st.size();
     if (starts && lens && order && cap >= st.size()) {
         std::memcpy(starts, st.data(), st.size() * sizeof(uint64_t));

@@ -227,6 +227,22 @@ def test_master_schedule_with_jump_ahead_equals_oracle(pkg, oracle, nsub, partit
     assert np.array_equal(np.sort(order), np.arange(nsub, dtype=np.uint32))
 
 
+def test_threaded_subsequence_count_of_fit_equals_the_chunker(pkg, oracle):
+    """fit() counts the sub-sequences with host threads (>= 2^18 users) and leaves the chunks to the device; sbr_host_schedule
+    cross-checks that count against its own one-thread chunker, which is pinned on the oracle here at a size that takes the
+    threaded path."""
+    rng = np.random.default_rng(5)
+    U, T = 300_000, 32
+    lens = rng.integers(0, 70, size=U)
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    ids = rng.integers(1, 50, size=int(ptr[-1])).astype(np.uint64)
+    data = pkg.CompressedInteractions.from_csr(ptr, ids, None, num_items=50)
+    starts, slens, order, _ = data.host_schedule(T, (1, 2, 3, 4))
+    ost, oln = oracle.subsequences(ptr, T)
+    assert np.array_equal(starts, ost) and np.array_equal(slens, oln)
+    assert np.array_equal(np.sort(order), np.arange(len(ost), dtype=np.uint32))
+
+
 def test_host_schedule_empty_is_no_interactions(pkg):
     ptr = np.array([0, 2, 3, 5], dtype=np.uint64)          # every user has <= 2 interactions: nothing survives the filter
     ids = np.array([1, 2, 3, 4, 5], dtype=np.uint64)
